@@ -1,0 +1,598 @@
+// sid_api.cu -- C ABI (include/sid_b200.h) over the sm_100a kernels.
+// No exceptions cross the boundary; every entry point returns a SID_* code.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sid_b200.h"
+#include "sid_common.cuh"
+#include "sid_pm_kernel.cuh"
+#include "sid_single_kernels.cuh"
+
+using namespace sid;
+
+namespace {
+
+constexpr size_t IMG_TAIL_SLACK = 4096;   // bytes readable past the last image row
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct sid_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    // resident image pair (padded pitch, 16-byte multiple)
+    DevBuf img1, img2;
+    int rows1 = 0, cols1 = 0, rows2 = 0, cols2 = 0;
+    long long pitch1 = 0, pitch2 = 0;
+    bool have_pair = false;
+    // per-call buffers
+    DevBuf pts, order, out, status, angles, scratch, counter, misc;
+    void *pin = nullptr;
+    size_t pin_cap = 0;
+    bool attr_set[3] = {false, false, false};
+    int attr_smem[3] = {0, 0, 0};
+};
+
+namespace {
+
+int fail(sid_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+int cuda_fail(sid_ctx *c, cudaError_t e, const char *what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return fail(c, SID_ECUDA, buf);
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
+    } while (0)
+
+int reserve(sid_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return SID_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SID_ENOMEM, "device allocation failed"); }
+    b.cap = want;
+    return SID_OK;
+}
+int reserve_pinned(sid_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pin_cap) return SID_OK;
+    if (ctx->pin) { cudaFreeHost(ctx->pin); ctx->pin = nullptr; ctx->pin_cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&ctx->pin, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SID_ENOMEM, "pinned allocation failed"); }
+    ctx->pin_cap = want;
+    return SID_OK;
+}
+
+long long padded_pitch(int cols) { return ((long long)cols + 15) / 16 * 16 + 16; }
+
+int upload_image(sid_ctx *ctx, DevBuf &buf, long long &pitch, const uint8_t *src, int rows, int cols,
+                 long long src_pitch, cudaMemcpyKind kind) {
+    if (!src || rows <= 0 || cols <= 0 || src_pitch < cols) return fail(ctx, SID_EINVAL, "bad image arguments");
+    pitch = padded_pitch(cols);
+    const size_t bytes = (size_t)pitch * rows + IMG_TAIL_SLACK;
+    const bool fresh = bytes > buf.cap;
+    int rc = reserve(ctx, buf, bytes);
+    if (rc) return rc;
+    if (fresh) CU(cudaMemsetAsync(buf.p, 0, buf.cap, ctx->stream));
+    CU(cudaMemcpy2DAsync(buf.p, (size_t)pitch, src, (size_t)src_pitch, (size_t)cols, (size_t)rows, kind, ctx->stream));
+    return SID_OK;
+}
+
+void gaussian_weights(double gw[5]) {
+    double w[9], sum = 0.0;
+    for (int k = -4; k <= 4; ++k) { w[k + 4] = std::exp(-0.5 * (double)(k * k)); sum += w[k + 4]; }
+    for (int k = 0; k < 9; ++k) w[k] /= sum;
+    for (int k = 0; k <= 4; ++k) gw[k] = w[4 + k];
+}
+
+int check_common(sid_ctx *ctx, int img_size, int n_angles, const double *angle_tab, int rot_order, int mtype) {
+    if (!ctx) return SID_EINVAL;
+    if (img_size < 2 || img_size > 128) return fail(ctx, SID_EUNSUPPORTED, "img_size must be in [2, 128]");
+    if (n_angles <= 0 || !angle_tab) return fail(ctx, SID_EINVAL, "need at least one angle and its table");
+    if (rot_order != 0 && rot_order != 1)
+        return fail(ctx, SID_EUNSUPPORTED, "rot_order must be 0 or 1 (higher spline orders need a full-image prefilter)");
+    if (mtype != SID_TM_CCOEFF_NORMED) return fail(ctx, SID_EUNSUPPORTED, "only TM_CCOEFF_NORMED (5) is implemented");
+    return SID_OK;
+}
+
+// shared launch path of sid_run / sid_run_device
+int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1, const double *d_c2fg,
+              const double *d_r2fg, const double *d_border, const int *d_order, int max_border, int typ_border,
+              int img_size, int n_angles, const double *d_angles, const double *d_tab, int rot_order,
+              unsigned flags, double *d_out, int *d_status) {
+    const int s = img_size;
+    const int hws = s / 2;
+    const int Wmax = 2 * hws + 2 * max_border + 1;
+    const int Rmax = Wmax - s + 1;
+    if (Rmax < 2) return fail(ctx, SID_EINVAL, "search window not larger than the template");
+    PmArgs a;
+    memset(&a, 0, sizeof a);
+    a.img1 = (const uint8_t *)ctx->img1.p; a.rows1 = ctx->rows1; a.cols1 = ctx->cols1; a.pitch1 = ctx->pitch1;
+    a.img2 = (const uint8_t *)ctx->img2.p; a.rows2 = ctx->rows2; a.cols2 = ctx->cols2; a.pitch2 = ctx->pitch2;
+    a.n = n;
+    a.c1 = d_c1; a.r1 = d_r1; a.c2fg = d_c2fg; a.r2fg = d_r2fg; a.border = d_border; a.order = d_order;
+    a.s = s; a.n_angles = n_angles; a.angles = d_angles; a.tab = d_tab;
+    a.rot_order = rot_order; a.flags = flags;
+    const double area = (double)s * (double)s;
+    a.inv_area = 1.0 / area;
+    a.sqrt_inv_area = std::sqrt(a.inv_area);
+    gaussian_weights(a.gw);
+    a.out = d_out; a.status = d_status;
+    a.max_rr = Rmax * Rmax;
+    a.max_hrw = Wmax * Rmax;
+    const int wpw = pm_window_pitch_words(Wmax);
+    a.win_words = Wmax * wpw + PM_WIN_SLACK;
+    const int nw = (s + 3) / 4;
+    int variant;                      // kernel specialisation by template width in words
+    if (nw == 9) variant = 0; else if (nw == 13) variant = 1; else variant = 2;
+    a.tpw = variant == 2 ? (s + 15) / 16 * 4 : (nw + 3) / 4 * 4;
+    a.ab = std::min(n_angles, PM_MAX_AB);
+    size_t smem = ((size_t)a.win_words + (size_t)a.ab * s * a.tpw) * 4;
+    while (smem > (size_t)ctx->max_smem_optin && a.ab > 1) {
+        --a.ab;
+        smem = ((size_t)a.win_words + (size_t)a.ab * s * a.tpw) * 4;
+    }
+    if (smem > (size_t)ctx->max_smem_optin)
+        return fail(ctx, SID_EUNSUPPORTED, "search window too large for the fused kernel (border too big)");
+
+    // CTA size: fill the CTA with thread tiles of a typical point
+    const int Rt = 2 * typ_border + (Wmax - 2 * max_border) - s + 1;
+    const int tx = pm_pick_tx(Rt);
+    const int ncg = (((Rt + 3) >> 2) + tx - 1) / tx;
+    const int nbatch = (n_angles + a.ab - 1) / a.ab;
+    const int per = (n_angles + nbatch - 1) / nbatch;
+    const long long ntiles = (long long)per * ncg * Rt * 4;
+    int threads = PM_THREADS;
+    double best_eff = -1.0;
+    for (int bs = 128; bs <= PM_THREADS; bs += 32) {
+        const double eff = (double)ntiles / (double)((ntiles + bs - 1) / bs * bs);
+        if (eff >= best_eff - 1e-9) { best_eff = eff; threads = bs; }
+    }
+
+    const void *kfn = variant == 0 ? (const void *)pm_points_kernel<9>
+                    : variant == 1 ? (const void *)pm_points_kernel<13>
+                                   : (const void *)pm_points_kernel<0>;
+    if (!ctx->attr_set[variant] || ctx->attr_smem[variant] < (int)smem) {
+        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+        ctx->attr_set[variant] = true;
+        ctx->attr_smem[variant] = (int)std::max(smem, (size_t)49152);
+    }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
+    if (occ < 1) return fail(ctx, SID_ECUDA, "kernel does not fit on an SM");
+    long long grid = (long long)ctx->sm_count * occ;
+    if (grid > n) grid = n;
+    if (grid < 1) grid = 1;
+
+    a.scratch_per_cta = pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab);
+    int rc = reserve(ctx, ctx->scratch, (size_t)a.scratch_per_cta * (size_t)grid);
+    if (rc) return rc;
+    a.scratch = (unsigned char *)ctx->scratch.p;
+    rc = reserve(ctx, ctx->counter, 256);
+    if (rc) return rc;
+    a.counter = (unsigned int *)ctx->counter.p;
+    CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
+
+    void *params[] = {(void *)&a};
+    CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, ctx->stream));
+    ctx->launches += 1;
+    return SID_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sid_version(void) { return "sea_ice_drift_b200 0.1 (sm_100a, IDP.4A exact-integer MCC)"; }
+
+int sid_create(sid_ctx **out, int device) {
+    if (!out) return SID_EINVAL;
+    *out = nullptr;
+    sid_ctx *ctx = new (std::nothrow) sid_ctx();
+    if (!ctx) return SID_ENOMEM;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return SID_ECUDA;
+    }
+    ctx->device = device;
+    ctx->stream = ctx->own_stream;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return SID_OK;
+}
+
+void sid_destroy(sid_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->img1, &ctx->img2, &ctx->pts, &ctx->order, &ctx->out, &ctx->status,
+                      &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *sid_last_error(const sid_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sid_set_stream(sid_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return SID_EINVAL;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SID_OK;
+}
+
+int sid_synchronize(sid_ctx *ctx) {
+    if (!ctx) return SID_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SID_OK;
+}
+
+int64_t sid_launch_count(const sid_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int set_pair_impl(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
+                         const uint8_t *img2, int rows2, int cols2, int64_t pitch2, cudaMemcpyKind kind) {
+    if (!ctx) return SID_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_pair = false;
+    int rc = upload_image(ctx, ctx->img1, ctx->pitch1, img1, rows1, cols1, pitch1, kind);
+    if (rc) return rc;
+    rc = upload_image(ctx, ctx->img2, ctx->pitch2, img2, rows2, cols2, pitch2, kind);
+    if (rc) return rc;
+    ctx->rows1 = rows1; ctx->cols1 = cols1; ctx->rows2 = rows2; ctx->cols2 = cols2;
+    ctx->have_pair = true;
+    return SID_OK;
+}
+
+int sid_set_pair(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
+                 const uint8_t *img2, int rows2, int cols2, int64_t pitch2) {
+    return set_pair_impl(ctx, img1, rows1, cols1, pitch1, img2, rows2, cols2, pitch2, cudaMemcpyHostToDevice);
+}
+int sid_set_pair_device(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
+                        const uint8_t *img2, int rows2, int cols2, int64_t pitch2) {
+    return set_pair_impl(ctx, img1, rows1, cols1, pitch1, img2, rows2, cols2, pitch2, cudaMemcpyDeviceToDevice);
+}
+
+static int upload_angles(sid_ctx *ctx, int n_angles, const double *angles, const double *angle_tab,
+                         const double **d_angles, const double **d_tab) {
+    const size_t bytes = (size_t)n_angles * 5 * sizeof(double);
+    int rc = reserve(ctx, ctx->angles, bytes);
+    if (rc) return rc;
+    std::vector<double> h((size_t)n_angles * 5);
+    for (int k = 0; k < n_angles; ++k) h[k] = angles ? angles[k] : (double)k;
+    memcpy(h.data() + n_angles, angle_tab, (size_t)n_angles * 4 * sizeof(double));
+    // small pageable copy: the runtime stages it before returning, so `h` may go out of scope
+    CU(cudaMemcpyAsync(ctx->angles.p, h.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *d_angles = (const double *)ctx->angles.p;
+    *d_tab = *d_angles + n_angles;
+    return SID_OK;
+}
+
+int sid_run(sid_ctx *ctx, int64_t n, const double *c1, const double *r1, const double *c2fg,
+            const double *r2fg, const double *border, int img_size, int n_angles, const double *angles,
+            const double *angle_tab, int rot_order, unsigned flags, int mtype, double *out, int *status) {
+    int rc = check_common(ctx, img_size, n_angles, angle_tab, rot_order, mtype);
+    if (rc) return rc;
+    if (!ctx->have_pair) return fail(ctx, SID_ENOPAIR, "sid_set_pair has not been called");
+    if (n < 0 || (n > 0 && (!c1 || !r1 || !c2fg || !r2fg || !border || !out)) || !angles)
+        return fail(ctx, SID_EINVAL, "null point array");
+    if (n == 0) return SID_OK;
+    if (n > 0x7fffffffLL) return fail(ctx, SID_EINVAL, "too many points");
+    CU(cudaSetDevice(ctx->device));
+
+    // borders: bound and processing order (largest window first, counting sort)
+    int max_border = 0;
+    std::vector<int> ib((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const double b = border[i];
+        int v = 0;
+        if (std::isfinite(b) && b >= 0.0 && b < 4096.0) v = (int)b;
+        ib[(size_t)i] = v;
+        max_border = std::max(max_border, v);
+    }
+    std::vector<int> hist((size_t)max_border + 2, 0);
+    for (int64_t i = 0; i < n; ++i) ++hist[(size_t)(max_border - ib[(size_t)i]) + 1];
+    for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
+    int typ_border = max_border;
+    {   // median border = typical point
+        long long half = n / 2;
+        for (int b = 0; b <= max_border; ++b) if (hist[(size_t)b + 1] > half) { typ_border = max_border - b; break; }
+    }
+
+    const size_t pts_bytes = (size_t)n * 5 * sizeof(double);
+    const size_t ord_bytes = (size_t)n * sizeof(int);
+    const size_t out_bytes = (size_t)n * 5 * sizeof(double);
+    const size_t st_bytes = (size_t)n * sizeof(int);
+    rc = reserve_pinned(ctx, pts_bytes + ord_bytes + out_bytes + st_bytes + 64);
+    if (rc) return rc;
+    if ((rc = reserve(ctx, ctx->pts, pts_bytes))) return rc;
+    if ((rc = reserve(ctx, ctx->order, ord_bytes))) return rc;
+    if ((rc = reserve(ctx, ctx->out, out_bytes))) return rc;
+    if ((rc = reserve(ctx, ctx->status, st_bytes))) return rc;
+
+    double *hp = (double *)ctx->pin;
+    memcpy(hp, c1, (size_t)n * 8); memcpy(hp + n, r1, (size_t)n * 8); memcpy(hp + 2 * n, c2fg, (size_t)n * 8);
+    memcpy(hp + 3 * n, r2fg, (size_t)n * 8); memcpy(hp + 4 * n, border, (size_t)n * 8);
+    int *hord = (int *)((char *)ctx->pin + pts_bytes);
+    for (int64_t i = 0; i < n; ++i) hord[hist[(size_t)(max_border - ib[(size_t)i])]++] = (int)i;
+    CU(cudaMemcpyAsync(ctx->pts.p, hp, pts_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->order.p, hord, ord_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const double *d_angles, *d_tab;
+    if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab))) return rc;
+
+    const double *dp = (const double *)ctx->pts.p;
+    rc = launch_pm(ctx, n, dp, dp + n, dp + 2 * n, dp + 3 * n, dp + 4 * n, (const int *)ctx->order.p,
+                   max_border, typ_border, img_size, n_angles, d_angles, d_tab, rot_order, flags,
+                   (double *)ctx->out.p, (int *)ctx->status.p);
+    if (rc) return rc;
+    double *hout = (double *)((char *)ctx->pin + pts_bytes + ord_bytes);
+    int *hst = (int *)((char *)hout + out_bytes);
+    CU(cudaMemcpyAsync(hout, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CU(cudaMemcpyAsync(hst, ctx->status.p, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    memcpy(out, hout, out_bytes);
+    if (status) memcpy(status, hst, st_bytes);
+    return SID_OK;
+}
+
+int sid_run_device(sid_ctx *ctx, int64_t n, const double *d_c1, const double *d_r1, const double *d_c2fg,
+                   const double *d_r2fg, const double *d_border, int max_border, int img_size, int n_angles,
+                   const double *angles, const double *angle_tab, int rot_order, unsigned flags, int mtype,
+                   double *d_out, int *d_status) {
+    int rc = check_common(ctx, img_size, n_angles, angle_tab, rot_order, mtype);
+    if (rc) return rc;
+    if (!ctx->have_pair) return fail(ctx, SID_ENOPAIR, "sid_set_pair has not been called");
+    if (n < 0 || (n > 0 && (!d_c1 || !d_r1 || !d_c2fg || !d_r2fg || !d_border || !d_out)) || !angles)
+        return fail(ctx, SID_EINVAL, "null point array");
+    if (n == 0) return SID_OK;
+    CU(cudaSetDevice(ctx->device));
+    if (max_border <= 0) {
+        std::vector<double> hb((size_t)n);
+        CU(cudaMemcpyAsync(hb.data(), d_border, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        max_border = 1;
+        for (double b : hb) if (std::isfinite(b) && b >= 0.0 && b < 4096.0) max_border = std::max(max_border, (int)b);
+    }
+    const double *d_angles, *d_tab;
+    if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab))) return rc;
+    return launch_pm(ctx, n, d_c1, d_r1, d_c2fg, d_r2fg, d_border, nullptr, max_border, max_border, img_size,
+                     n_angles, d_angles, d_tab, rot_order, flags, d_out, d_status);
+}
+
+// ------------------------------------------------------------------ single-call entry points
+
+int sid_get_template(sid_ctx *ctx, const uint8_t *img, int rows, int cols, int64_t pitch, double c, double r,
+                     const double *angle_tab, int s, int rot_order, uint8_t *out) {
+    if (!ctx) return SID_EINVAL;
+    if (!img || !out || !angle_tab || s <= 0 || s > 4096) return fail(ctx, SID_EINVAL, "bad get_template arguments");
+    if (rot_order != 0 && rot_order != 1) return fail(ctx, SID_EUNSUPPORTED, "rot_order must be 0 or 1");
+    CU(cudaSetDevice(ctx->device));
+    long long dp;
+    int rc = upload_image(ctx, ctx->img1, dp, img, rows, cols, pitch, cudaMemcpyHostToDevice);
+    ctx->have_pair = false;
+    if (rc) return rc;
+    const size_t tb = (size_t)s * s;
+    if ((rc = reserve(ctx, ctx->misc, tb + 64 + 4 * 8 + 16))) return rc;
+    uint8_t *d_t = (uint8_t *)ctx->misc.p;
+    const size_t off_tab = (tb + 63) / 64 * 64;
+    double *d_tab = (double *)(d_t + off_tab);
+    uint32_t *d_stats = (uint32_t *)(d_tab + 4);
+    CU(cudaMemcpyAsync(d_tab, angle_tab, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_stats, 0, 12, ctx->stream));
+    templates_kernel<<<1, 256, 0, ctx->stream>>>((const uint8_t *)ctx->img1.p, rows, cols, dp, c, r, d_tab, s, rot_order, d_t, d_stats);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_t, tb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SID_OK;
+}
+
+// NCC map of a device image/template pair into d_out; isum/isq/tstats are device scratch.
+static int match_on_device(sid_ctx *ctx, const uint8_t *d_img, int H, int W, long long pitch, const uint8_t *d_tpl,
+                           int th, int tw, long long tp, uint32_t *d_isum, uint32_t *d_isq, bool integrals_ready,
+                           uint32_t *d_tstats, float *d_out) {
+    const int RH = H - th + 1, RW = W - tw + 1;
+    if (!integrals_ready) {
+        integral_rows_kernel<<<(H + 1 + 127) / 128, 128, 0, ctx->stream>>>(d_img, H, W, pitch, d_isum, d_isq);
+        integral_cols_kernel<<<(W + 1 + 127) / 128, 128, 0, ctx->stream>>>(H, W, d_isum, d_isq);
+        ctx->launches += 2;
+    }
+    CU(cudaMemsetAsync(d_tstats, 0, 8, ctx->stream));
+    template_sums_kernel<<<std::min(64, (th * tw + 255) / 256), 256, 0, ctx->stream>>>(d_tpl, th, tw, tp, d_tstats);
+    MtArgs a;
+    a.img = d_img; a.H = H; a.W = W; a.pitch = pitch;
+    a.tpl = d_tpl; a.th = th; a.tw = tw; a.tp = tp;
+    a.isum = d_isum; a.isq = d_isq; a.tstats = d_tstats;
+    const double area = (double)th * (double)tw;
+    a.inv_area = 1.0 / area; a.sqrt_inv_area = std::sqrt(a.inv_area);
+    a.out = d_out;
+    a.tpw = (tw + 15) / 16 * 4;
+    int n16 = (MT_COLS + tw + 3 + 15) / 16 + 1;
+    if ((n16 & 1) == 0) ++n16;
+    a.wpw = n16 * 4;
+    const size_t smem = ((size_t)(MT_ROWS + th - 1) * a.wpw + PM_WIN_SLACK + (size_t)th * a.tpw) * 4;
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SID_EUNSUPPORTED, "template too large for match_template");
+    CU(cudaFuncSetAttribute(match_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+    dim3 grid((RW + MT_COLS - 1) / MT_COLS, (RH + MT_ROWS - 1) / MT_ROWS);
+    match_template_kernel<<<grid, 256, smem, ctx->stream>>>(a);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return SID_OK;
+}
+
+int sid_match_template(sid_ctx *ctx, const uint8_t *img, int H, int W, int64_t pitch, const uint8_t *tpl,
+                       int th, int tw, int64_t tpitch, int method, float *out) {
+    if (!ctx) return SID_EINVAL;
+    if (method != SID_TM_CCOEFF_NORMED) return fail(ctx, SID_EUNSUPPORTED, "only TM_CCOEFF_NORMED (5) is implemented");
+    if (!img || !tpl || !out || th <= 0 || tw <= 0 || H < th || W < tw || pitch < W || tpitch < tw)
+        return fail(ctx, SID_EINVAL, "bad match_template arguments (image must not be smaller than the template)");
+    if ((long long)th * tw > 32768) return fail(ctx, SID_EUNSUPPORTED, "template area above 32768 pixels");
+    CU(cudaSetDevice(ctx->device));
+    long long dp;
+    int rc = upload_image(ctx, ctx->img2, dp, img, H, W, pitch, cudaMemcpyHostToDevice);
+    ctx->have_pair = false;
+    if (rc) return rc;
+    const int RH = H - th + 1, RW = W - tw + 1;
+    const size_t int_bytes = (size_t)(H + 1) * (W + 1) * 4;
+    const size_t tpl_bytes = ((size_t)th * tw + 255) / 256 * 256;
+    const size_t out_bytes = (size_t)RH * RW * 4;
+    if ((rc = reserve(ctx, ctx->misc, 2 * int_bytes + tpl_bytes + out_bytes + 1024))) return rc;
+    unsigned char *base = (unsigned char *)ctx->misc.p;
+    uint32_t *d_isum = (uint32_t *)base, *d_isq = (uint32_t *)(base + int_bytes);
+    uint8_t *d_tpl = base + 2 * int_bytes;
+    float *d_out = (float *)(base + 2 * int_bytes + tpl_bytes);
+    uint32_t *d_ts = (uint32_t *)(base + 2 * int_bytes + tpl_bytes + out_bytes);
+    d_ts = (uint32_t *)(((uintptr_t)d_ts + 15) & ~(uintptr_t)15);
+    CU(cudaMemcpy2DAsync(d_tpl, (size_t)tw, tpl, (size_t)tpitch, (size_t)tw, (size_t)th, cudaMemcpyHostToDevice, ctx->stream));
+    rc = match_on_device(ctx, (const uint8_t *)ctx->img2.p, H, W, dp, d_tpl, th, tw, tw, d_isum, d_isq, false, d_ts, d_out);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return SID_OK;
+}
+
+int sid_get_hessian(sid_ctx *ctx, const float *ccm, int rows, int cols, unsigned flags, float *out) {
+    if (!ctx) return SID_EINVAL;
+    if (!ccm || !out || rows < 2 || cols < 2) return fail(ctx, SID_EINVAL, "get_hessian needs a map of at least 2 x 2");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)rows * cols, b = n * 4;
+    int rc = reserve(ctx, ctx->misc, 4 * b + 64);
+    if (rc) return rc;
+    float *d = (float *)ctx->misc.p;
+    CU(cudaMemcpyAsync(d, ccm, b, cudaMemcpyHostToDevice, ctx->stream));
+    HesArgs a;
+    a.ccm = d; a.rows = rows; a.cols = cols; a.flags = flags; gaussian_weights(a.gw);
+    a.tmp_a = d + n; a.tmp_b = d + 2 * n; a.out = d + 3 * n;
+    hessian_map_kernel<<<1, 1024, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, a.out, b, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return SID_OK;
+}
+
+int sid_rotate_and_match(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_t pitch1, double c1,
+                         double r1, int img_size, const uint8_t *image2, int H, int W, int64_t pitch2,
+                         int n_angles, const double *angle_tab, int rot_order, unsigned flags, int mtype,
+                         int *valid, double *dc, double *dr, int *best_angle_idx, float *best_r, float *best_h,
+                         float *best_result, uint8_t *best_template) {
+    int rc = check_common(ctx, img_size, n_angles, angle_tab, rot_order, mtype);
+    if (rc) return rc;
+    if (!valid || !dc || !dr || !best_angle_idx || !best_r || !best_h) return fail(ctx, SID_EINVAL, "null output pointer");
+    const int s = img_size;
+    if (!img1 || !image2 || H < s + 1 || W < s + 1)
+        return fail(ctx, SID_EINVAL, "search window must exceed the template by at least one pixel in each axis");
+    CU(cudaSetDevice(ctx->device));
+    long long dp1, dp2;
+    ctx->have_pair = false;
+    if ((rc = upload_image(ctx, ctx->img1, dp1, img1, rows1, cols1, pitch1, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = upload_image(ctx, ctx->img2, dp2, image2, H, W, pitch2, cudaMemcpyHostToDevice))) return rc;
+    const int RH = H - s + 1, RW = W - s + 1;
+    const size_t rr = (size_t)RH * RW;
+    const size_t int_bytes = ((size_t)(H + 1) * (W + 1) * 4 + 255) / 256 * 256;
+    const size_t tpl_bytes = ((size_t)n_angles * s * s + 255) / 256 * 256;
+    const size_t map_bytes = (rr * 4 + 255) / 256 * 256;
+    const size_t small = 4096 + (size_t)n_angles * 64;
+    if ((rc = reserve(ctx, ctx->misc, 2 * int_bytes + tpl_bytes + 5 * map_bytes + small))) return rc;
+    unsigned char *base = (unsigned char *)ctx->misc.p;
+    uint32_t *d_isum = (uint32_t *)base, *d_isq = (uint32_t *)(base + int_bytes);
+    uint8_t *d_tpl = base + 2 * int_bytes;
+    float *d_maps = (float *)(base + 2 * int_bytes + tpl_bytes);     // 0,1: ping-pong; 2,3,4: tmp_a, tmp_b, hes
+    unsigned char *sm = base + 2 * int_bytes + tpl_bytes + 5 * map_bytes;
+    double *d_tab = (double *)sm;                                     // n_angles * 4 doubles
+    uint32_t *d_stats = (uint32_t *)(sm + (size_t)n_angles * 32);     // n_angles * 3
+    uint32_t *d_ts = d_stats + (size_t)n_angles * 3 + 4;              // 2
+    unsigned long long *d_key = (unsigned long long *)(((uintptr_t)(d_ts + 4) + 15) & ~(uintptr_t)15);
+    float *d_peak = (float *)(d_key + 2);
+    const size_t mstride = map_bytes / 4;
+
+    CU(cudaMemcpyAsync(d_tab, angle_tab, (size_t)n_angles * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_stats, 0, (size_t)n_angles * 12, ctx->stream));
+    templates_kernel<<<n_angles, 256, 0, ctx->stream>>>((const uint8_t *)ctx->img1.p, rows1, cols1, dp1, c1, r1, d_tab, s,
+                                                       rot_order, d_tpl, d_stats);
+    ctx->launches += 1;
+    std::vector<uint32_t> hstats((size_t)n_angles * 3);
+    CU(cudaMemcpyAsync(hstats.data(), d_stats, (size_t)n_angles * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    *valid = 1;
+    for (int a = 0; a < n_angles; ++a) if (hstats[(size_t)a * 3 + 2]) *valid = 0;
+    if (!*valid) {
+        *dc = NAN; *dr = NAN; *best_angle_idx = -1; *best_r = NAN; *best_h = NAN;
+        return SID_OK;
+    }
+    float br = -INFINITY; int ba = -1, bslot = -1; uint32_t bidx = 0;
+    for (int a = 0; a < n_angles; ++a) {
+        const int slot = (bslot == 0) ? 1 : 0;
+        float *d_map = d_maps + (size_t)slot * mstride;
+        rc = match_on_device(ctx, (const uint8_t *)ctx->img2.p, H, W, dp2, d_tpl + (size_t)a * s * s, s, s, s,
+                             d_isum, d_isq, a > 0, d_ts, d_map);
+        if (rc) return rc;
+        argmax_kernel<<<1, 1024, 0, ctx->stream>>>(d_map, (int)rr, d_key);
+        ctx->launches += 1;
+        unsigned long long key = 0;
+        CU(cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaGetLastError());
+        const uint32_t hi = (uint32_t)(key >> 32);
+        const uint32_t ubits = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
+        float v; memcpy(&v, &ubits, 4);
+        if (v > br) { br = v; ba = a; bslot = slot; bidx = 0xffffffffu - (uint32_t)(key & 0xffffffffull); }
+    }
+    if (ba < 0) {
+        *valid = 0; *dc = NAN; *dr = NAN; *best_angle_idx = -1; *best_r = NAN; *best_h = NAN;
+        return SID_OK;
+    }
+    PeakArgs pa;
+    pa.best = d_maps + (size_t)bslot * mstride; pa.rows = RH; pa.cols = RW; pa.idx = (int)bidx; pa.r = br; pa.flags = flags;
+    gaussian_weights(pa.gw);
+    pa.tmp_a = d_maps + 2 * mstride; pa.tmp_b = d_maps + 3 * mstride; pa.hes = d_maps + 4 * mstride; pa.out = d_peak;
+    peak_stats_kernel<<<1, 1024, 0, ctx->stream>>>(pa);
+    ctx->launches += 1;
+    float hp[2];
+    CU(cudaMemcpyAsync(hp, d_peak, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (best_result) CU(cudaMemcpyAsync(best_result, pa.best, rr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (best_template) CU(cudaMemcpyAsync(best_template, d_tpl + (size_t)ba * s * s, (size_t)s * s, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    const int bi = (int)(bidx / (uint32_t)RW), bj = (int)(bidx % (uint32_t)RW);
+    *dr = (double)bi - (double)(H - s) / 2.0;
+    *dc = (double)bj - (double)(W - s) / 2.0;
+    *best_angle_idx = ba;
+    *best_r = hp[0];
+    *best_h = hp[1];
+    return SID_OK;
+}
+
+}  // extern "C"

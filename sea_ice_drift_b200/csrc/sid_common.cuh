@@ -1,0 +1,296 @@
+// sid_common.cuh -- device helpers shared by all kernels of the MCC hot path.
+//
+// Arithmetic contract (what makes results reproducible bit for bit on any IEEE-754 machine):
+//   * correlation numerators, window sums and template sums are exact integers;
+//   * everything OpenCV's common_matchTemplate does in double is done here in double
+//     with explicit round-to-nearest intrinsics, so the compiler can never contract
+//     a multiply-add into an FMA (an FMA rounds once and would change the last bit);
+//   * template coordinates follow scipy.ndimage.affine_transform's evaluation order
+//     (off + i*m0 + j*m1, left to right) in double, again without FMA;
+//   * np.gradient / np.hypot / np.median / np.std run in float32 as NumPy does.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include <math.h>
+
+namespace sid {
+
+// ---------------------------------------------------------------- float <-> sortable key
+__device__ __forceinline__ uint32_t f32_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------- block reductions
+// All take a small shared scratch area and are called by every thread of the CTA.
+struct BlockScratch {
+    double red[32];
+    uint32_t hist[256];
+    uint32_t sel[2];
+};
+
+__device__ __forceinline__ double block_sum(double v, BlockScratch &bs) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) bs.red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += bs.red[w];
+    return t;
+}
+
+// k-th smallest (0-based) of n floats: 4-pass MSD radix select on sortable keys.
+__device__ float block_select(const float *__restrict__ d, int n, int k, BlockScratch &bs) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t prefix = 0, mask = 0;
+    uint32_t kk = (uint32_t)k;
+    const int iters = (n + nt - 1) / nt;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += nt) bs.hist[i] = 0;
+        __syncthreads();
+        for (int it = 0; it < iters; ++it) {
+            const int i = it * nt + tid;
+            uint32_t bin = 0xffffffffu;
+            if (i < n) {
+                const uint32_t key = f32_key(d[i]);
+                if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+            }
+            // warp-aggregated histogram update: one atomic per distinct bin per warp
+            const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&bs.hist[bin], __popc(peers));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t h[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = bs.hist[lane * 8 + j]; s += h[j]; }
+            uint32_t incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t excl = incl - s;
+            if (kk >= excl && kk < incl) {
+                uint32_t c = excl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (kk < c + h[j]) { bs.sel[0] = lane * 8 + j; bs.sel[1] = kk - c; break; }
+                    c += h[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= bs.sel[0] << shift;
+        mask |= 0xffu << shift;
+        kk = bs.sel[1];
+        __syncthreads();
+    }
+    return key_f32(prefix);
+}
+
+// np.median of n float32 values (no NaN handling needed: NCC maps are finite).
+__device__ float block_median(const float *__restrict__ d, int n, BlockScratch &bs) {
+    if (n & 1) return block_select(d, n, n / 2, bs);
+    const float a = block_select(d, n, n / 2 - 1, bs);
+    const float b = block_select(d, n, n / 2, bs);
+    return __fmul_rn(__fadd_rn(a, b), 0.5f);
+}
+
+// np.std (float32 input, ddof=0): float32 mean / deviations / squares, sums in double.
+__device__ float block_std(const float *__restrict__ d, int n, BlockScratch &bs) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double s = 0.0;
+    for (int i = tid; i < n; i += nt) s += (double)d[i];
+    s = block_sum(s, bs);
+    const float mean = __double2float_rn(s / (double)n);
+    double q = 0.0;
+    for (int i = tid; i < n; i += nt) {
+        const float dv = __fsub_rn(d[i], mean);
+        q += (double)__fmul_rn(dv, dv);
+    }
+    q = block_sum(q, bs);
+    const float var = __double2float_rn(q / (double)n);
+    return __fsqrt_rn(var);
+}
+
+// ---------------------------------------------------------------- NCC normalisation
+// cv::meanStdDev + the template part of common_matchTemplate.
+struct TemplStats {
+    double mean;   // templMean
+    double norm;   // templNorm = sqrt(sdv^2) / sqrt(invArea)
+    int flat;      // sdv^2 < DBL_EPSILON -> whole map = 1
+};
+
+__device__ __forceinline__ TemplStats templ_stats(uint32_t tsum, uint32_t tsq, double inv_area, double sqrt_inv_area) {
+    TemplStats st;
+    st.mean = __dmul_rn((double)tsum, inv_area);
+    double var = __dsub_rn(__dmul_rn((double)tsq, inv_area), __dmul_rn(st.mean, st.mean));
+    if (var < 0.0) var = 0.0;
+    const double sdv = __dsqrt_rn(var);
+    const double tn = __dmul_rn(sdv, sdv);
+    st.flat = tn < DBL_EPSILON;
+    st.norm = __ddiv_rn(__dsqrt_rn(tn), sqrt_inv_area);
+    return st;
+}
+
+// sqrt(max(winSqSum - winSum^2/N, 0)), or 0 under OpenCV's "avoid rounding errors" rule
+__device__ __forceinline__ double window_den(uint32_t wsum, uint32_t wsq, double inv_area) {
+    const double t = (double)wsum;
+    const double mean2 = __dmul_rn(__dmul_rn(t, t), inv_area);
+    const double sum2 = (double)wsq;
+    double diff2 = __dsub_rn(sum2, mean2);
+    if (diff2 < 0.0) diff2 = 0.0;
+    double thr = __dmul_rn(10.0 * (double)FLT_EPSILON, sum2);
+    if (thr > 0.5) thr = 0.5;
+    return diff2 <= thr ? 0.0 : __dsqrt_rn(diff2);
+}
+
+__device__ __forceinline__ float ncc_value(int64_t corr, uint32_t wsum, double wden, const TemplStats &st) {
+    if (st.flat) return 1.0f;
+    double num = __dsub_rn((double)corr, __dmul_rn((double)wsum, st.mean));
+    const double t = __dmul_rn(wden, st.norm);
+    const double an = fabs(num);
+    if (an < t) num = __ddiv_rn(num, t);
+    else if (an < __dmul_rn(t, 1.125)) num = num > 0.0 ? 1.0 : -1.0;
+    else num = 0.0;
+    return __double2float_rn(num);
+}
+
+// ---------------------------------------------------------------- rotated template sample
+// get_template (reference pmlib.py:89-115) for output pixel (i, j).
+__device__ __forceinline__ uint8_t template_pixel(const uint8_t *__restrict__ img, int rows, int cols, int64_t pitch,
+                                                  double off0, double off1, double cs, double sn,
+                                                  int i, int j, int order) {
+    const double di = (double)i, dj = (double)j;
+    const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), __dmul_rn(dj, sn));
+    const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), __dmul_rn(dj, cs));
+    if (!(row >= 0.0 && row <= (double)(rows - 1) && col >= 0.0 && col <= (double)(cols - 1))) return 0;
+    if (order == 0) {
+        long long ri = __double2ll_rd(__dadd_rn(row, 0.5));
+        long long ci = __double2ll_rd(__dadd_rn(col, 0.5));
+        if (ri > rows - 1) ri = rows - 1;
+        if (ci > cols - 1) ci = cols - 1;
+        return __ldg(img + ri * pitch + ci);
+    }
+    const double fr = floor(row), fc = floor(col);
+    const long long r0 = (long long)fr, c0 = (long long)fc;
+    const double fy = __dsub_rn(row, fr), fx = __dsub_rn(col, fc);
+    const double wy0 = __dsub_rn(1.0, fy), wx0 = __dsub_rn(1.0, fx);
+    const long long r1 = r0 + 1 > rows - 1 ? rows - 1 : r0 + 1;
+    const long long c1 = c0 + 1 > cols - 1 ? cols - 1 : c0 + 1;
+    double t = 0.0;
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r0 * pitch + c0), wy0), wx0));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r0 * pitch + c1), wy0), fx));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r1 * pitch + c0), fy), wx0));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r1 * pitch + c1), fy), fx));
+    t = t > 0.0 ? __dadd_rn(t, 0.5) : 0.0;
+    if (t > 255.0) t = 255.0;
+    return (uint8_t)t;
+}
+
+// ---------------------------------------------------------------- Hessian pieces
+// np.gradient along one axis (unit spacing, edge_order=1) at position `i` of a line
+// of `n` float32 samples spaced `stride` apart.
+__device__ __forceinline__ float grad_at(const float *__restrict__ line, int n, int stride, int i) {
+    if (i == 0) return __fsub_rn(line[stride], line[0]);
+    if (i == n - 1) return __fsub_rn(line[(n - 1) * stride], line[(n - 2) * stride]);
+    return __fmul_rn(__fsub_rn(line[(i + 1) * stride], line[(i - 1) * stride]), 0.5f);
+}
+// gradient of the gradient along the same axis
+__device__ __forceinline__ float grad2_at(const float *__restrict__ line, int n, int stride, int i) {
+    if (i == 0) return __fsub_rn(grad_at(line, n, stride, 1), grad_at(line, n, stride, 0));
+    if (i == n - 1) return __fsub_rn(grad_at(line, n, stride, n - 1), grad_at(line, n, stride, n - 2));
+    return __fmul_rn(__fsub_rn(grad_at(line, n, stride, i + 1), grad_at(line, n, stride, i - 1)), 0.5f);
+}
+// hes = hypot(d2/dx2, d2/dy2) at (y, x) of a rows x cols map
+__device__ __forceinline__ float hessian_at(const float *__restrict__ f, int rows, int cols, int y, int x) {
+    const double a = (double)grad2_at(f + (size_t)y * cols, cols, 1, x);
+    const double b = (double)grad2_at(f + x, rows, cols, y);
+    return __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b))));
+}
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    // scipy 'reflect': (d c b a | a b c d | d c b a)
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i - 1;
+        if (i >= n) i = 2 * n - 1 - i;
+    }
+    return i;
+}
+// one pass of gaussian_filter(sigma=1) (9 taps, weights gw[0..4] = centre..edge) along `axis`
+__device__ __forceinline__ float gauss_at(const float *__restrict__ f, int rows, int cols, int y, int x, int axis,
+                                          const double *gw) {
+    double acc = __dmul_rn(gw[0], (double)f[(size_t)y * cols + x]);
+#pragma unroll
+    for (int k = 1; k <= 4; ++k) {
+        double a, b;
+        if (axis == 0) {
+            a = (double)f[(size_t)reflect_index(y - k, rows) * cols + x];
+            b = (double)f[(size_t)reflect_index(y + k, rows) * cols + x];
+        } else {
+            a = (double)f[(size_t)y * cols + reflect_index(x - k, cols)];
+            b = (double)f[(size_t)y * cols + reflect_index(x + k, cols)];
+        }
+        acc = __dadd_rn(acc, __dmul_rn(gw[k], __dadd_rn(a, b)));
+    }
+    return __double2float_rn(acc);
+}
+
+// Tail of rotate_and_match (reference pmlib.py:167-172): Hessian at the peak and the
+// optional normalisations.  `best` is the winning NCC map; tmp_a/tmp_b/hes are scratch
+// maps of the same size.  Every thread of the CTA calls this; results valid in all.
+struct PeakStats { float h; float r; };
+__device__ PeakStats peak_statistics(const float *__restrict__ best, int rows, int cols, int peak_idx, float peak_r,
+                                     unsigned flags, const double *gw,
+                                     float *__restrict__ tmp_a, float *__restrict__ tmp_b, float *__restrict__ hes,
+                                     BlockScratch &bs) {
+    const int tid = threadIdx.x, nt = blockDim.x, n = rows * cols;
+    const float *src = best;
+    if (flags & 2u) {               // hes_smth
+        for (int k = tid; k < n; k += nt) tmp_a[k] = gauss_at(best, rows, cols, k / cols, k % cols, 0, gw);
+        __syncthreads();
+        for (int k = tid; k < n; k += nt) tmp_b[k] = gauss_at(tmp_a, rows, cols, k / cols, k % cols, 1, gw);
+        __syncthreads();
+        src = tmp_b;
+    }
+    for (int k = tid; k < n; k += nt) hes[k] = hessian_at(src, rows, cols, k / cols, k % cols);
+    __syncthreads();
+    PeakStats ps;
+    ps.h = hes[peak_idx];
+    ps.r = peak_r;
+    if (flags & 1u) {               // hes_norm
+        const float med = block_median(hes, n, bs);
+        const float sd = block_std(hes, n, bs);
+        ps.h = __fdiv_rn(__fsub_rn(ps.h, med), sd);
+    }
+    if (flags & 4u) {               // mcc_norm
+        const float med = block_median(best, n, bs);
+        const float sd = block_std(best, n, bs);
+        ps.r = __fdiv_rn(__fsub_rn(peak_r, med), sd);
+    }
+    return ps;
+}
+
+// ---------------------------------------------------------------- argmax helpers
+// key = (sortable value << 32) | (~flat_index): max() gives the largest value and,
+// among equal values, the lowest row-major index (np.argmax semantics).
+__device__ __forceinline__ unsigned long long peak_key(float v, uint32_t idx) {
+    return ((unsigned long long)f32_key(v) << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+        k = other > k ? other : k;
+    }
+    return k;
+}
+
+}  // namespace sid

@@ -1,0 +1,413 @@
+// sid_pm_kernel.cuh -- the fused, batched pattern-matching kernel.
+//
+// One persistent CTA per grid point (work-stealing over an LPT-ordered list) does
+// everything the reference's use_mcc (pmlib.py:176-212) does for that point:
+//
+//   1. cut the search window of image 2 (pmlib.py:200-202) into shared memory,
+//      re-aligned to 32-bit words with a funnel shift while loading;
+//   2. window sums / sums of squares for every displacement with two sliding-sum
+//      passes (exact integers), folded into sqrt(max(sq - s^2/N, 0)) once per point;
+//   3. for every angle (batches of <= PM_MAX_AB held in shared memory at once):
+//      gather the rotated template from image 1 (get_template, pmlib.py:89-115),
+//      zero-pixel check (pmlib.py:152-154), then the correlation numerators with
+//      exact-integer IDP.4A: each thread owns one output row, one column class
+//      (x mod 4) and TX outputs at stride 4, so every window word it needs is one
+//      SHF of two aligned words and every template word is a warp-wide broadcast;
+//      OpenCV's TM_CCOEFF_NORMED normalisation in FP64 without FMA contraction;
+//      running argmax with np.argmax tie rules; best angle with the reference's
+//      strict '>' rule (pmlib.py:158-165);
+//   4. Hessian at the peak, median (radix select) / std normalisation, optional
+//      mcc_norm (pmlib.py:167-172) and the displacement bookkeeping (pmlib.py:168-169,
+//      209-210).
+//
+// Result-sized arrays (window statistics, NCC maps) live in a per-CTA global scratch
+// slab that stays L2-resident; only O(R^2) traffic per angle goes there, against
+// O(R^2 s^2) integer MACs out of shared memory / registers.
+#pragma once
+#include "sid_common.cuh"
+
+namespace sid {
+
+constexpr int PM_THREADS = 256;
+constexpr int PM_MAX_AB = 4;      // angles whose templates sit in shared memory together
+constexpr int PM_SEG = 16;        // outputs per sliding-sum work item
+constexpr int PM_WIN_SLACK = 64;  // words readable past the staged window
+
+struct PmArgs {
+    const uint8_t *img1; int rows1, cols1; long long pitch1;
+    const uint8_t *img2; int rows2, cols2; long long pitch2;
+    long long n;
+    const double *c1, *r1, *c2fg, *r2fg, *border;
+    const int *order;             // optional processing order (largest windows first)
+    int s;                        // img_size
+    int n_angles;
+    const double *angles;         // device, n_angles
+    const double *tab;            // device, n_angles x 4
+    int rot_order;
+    unsigned flags;
+    double inv_area, sqrt_inv_area;
+    double gw[5];                 // gaussian_filter(sigma=1) weights, centre..edge
+    double *out;                  // n x 5
+    int *status;                  // optional
+    unsigned char *scratch;
+    unsigned long long scratch_per_cta;
+    int max_rr;                   // capacity of one result map (elements)
+    int max_hrw;                  // capacity of the horizontal-sum arrays
+    int win_words;                // capacity of the staged window (32-bit words, incl. slack)
+    int tpw;                      // template row pitch in words (multiple of 4)
+    int ab;                       // angles per batch
+    unsigned int *counter;        // work-stealing cursor
+};
+
+__host__ __device__ inline int pm_window_pitch_words(int W) {
+    int n16 = (W + 4 + 15) / 16;          // 16-byte units, with room for the shifted tail
+    if ((n16 & 1) == 0) ++n16;            // odd multiple of 16 B -> 8 consecutive rows hit 8 distinct bank groups
+    return n16 * 4;
+}
+
+// ---- correlation numerators for one thread tile -----------------------------------
+// acc[tx] += sum_i sum_jj dp4a(window word (row y+i, word q0+tx+jj, byte shift p), template word (i, jj))
+template <int TX, int NW>
+__device__ __forceinline__ void mac_rows(const uint32_t *__restrict__ wrow, int wpw,
+                                         const uint32_t *__restrict__ trow, int tpw,
+                                         int s, int sh, unsigned (&acc)[TX]) {
+    for (int i = 0; i < s; ++i) {
+        uint32_t w[TX + NW];
+#pragma unroll
+        for (int k = 0; k < TX + NW; ++k) w[k] = wrow[k];
+#pragma unroll
+        for (int k = 0; k < TX + NW - 1; ++k) w[k] = __funnelshift_r(w[k], w[k + 1], sh);
+        uint32_t t[(NW + 3) / 4 * 4];
+#pragma unroll
+        for (int k = 0; k < (NW + 3) / 4; ++k) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(trow + 4 * k);
+            t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < NW; ++jj)
+#pragma unroll
+            for (int tx = 0; tx < TX; ++tx) acc[tx] = __dp4a(w[tx + jj], t[jj], acc[tx]);
+        wrow += wpw;
+        trow += tpw;
+    }
+}
+
+// any template width: 16 template bytes (4 words) at a time
+template <int TX>
+__device__ __forceinline__ void mac_rows_any(const uint32_t *__restrict__ wrow, int wpw,
+                                             const uint32_t *__restrict__ trow, int tpw,
+                                             int s, int nchunk, int sh, unsigned (&acc)[TX]) {
+    for (int i = 0; i < s; ++i) {
+        for (int c = 0; c < nchunk; ++c) {
+            uint32_t w[TX + 4];
+#pragma unroll
+            for (int k = 0; k < TX + 4; ++k) w[k] = wrow[4 * c + k];
+#pragma unroll
+            for (int k = 0; k < TX + 3; ++k) w[k] = __funnelshift_r(w[k], w[k + 1], sh);
+            const uint4 v = *reinterpret_cast<const uint4 *>(trow + 4 * c);
+            const uint32_t t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int tx = 0; tx < TX; ++tx) acc[tx] = __dp4a(w[tx + jj], t[jj], acc[tx]);
+        }
+        wrow += wpw;
+        trow += tpw;
+    }
+}
+
+struct PmShared {
+    BlockScratch bs;
+    TemplStats st[PM_MAX_AB];
+    unsigned long long key[PM_MAX_AB];
+    uint32_t tsum[PM_MAX_AB], tsq[PM_MAX_AB];
+    int slot[PM_MAX_AB];
+    int haszero;
+    unsigned int point;
+    float best_r;
+    int best_a, best_idx, best_slot;
+};
+
+// All tiles of one angle batch.  NW > 0: compile-time template width in words.
+template <int TX, int NW>
+__device__ __forceinline__ void pm_tiles(const uint32_t *__restrict__ win32, int wpw,
+                                         const uint32_t *__restrict__ tpl32, int tpw, int s,
+                                         int nb, int RH, int RW,
+                                         const uint32_t *__restrict__ wsum, const double *__restrict__ wden,
+                                         float *__restrict__ maps, int max_rr, PmShared &S) {
+    const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    const int nwc = (RW + 3) >> 2;
+    const int ncg = (nwc + TX - 1) / TX;
+    const int ntiles = nb * ncg * RH * 4;
+    const int nchunk = (s + 15) / 16;
+    for (int base = 0; base < ntiles; base += nt) {
+        const int t = base + tid;
+        int my_ai = -1;
+        unsigned long long key = 0ull;
+        if (t < ntiles) {
+            const int p = t & 3;
+            int u = t >> 2;
+            const int y = u % RH; u /= RH;
+            const int cg = u % ncg;
+            const int ai = u / ncg;
+            const int q0 = cg * TX;
+            unsigned acc[TX];
+#pragma unroll
+            for (int k = 0; k < TX; ++k) acc[k] = 0u;
+            const uint32_t *wrow = win32 + y * wpw + q0;
+            const uint32_t *trow = tpl32 + ai * s * tpw;
+            if (NW > 0) mac_rows<TX, (NW > 0 ? NW : 1)>(wrow, wpw, trow, tpw, s, 8 * p, acc);
+            else mac_rows_any<TX>(wrow, wpw, trow, tpw, s, nchunk, 8 * p, acc);
+            const TemplStats st = S.st[ai];
+            float *map = maps + (size_t)S.slot[ai] * max_rr;
+            my_ai = ai;
+#pragma unroll
+            for (int tx = 0; tx < TX; ++tx) {
+                const int x = 4 * (q0 + tx) + p;
+                if (x < RW) {
+                    const int idx = y * RW + x;
+                    const float v = ncc_value((long long)acc[tx], wsum[idx], wden[idx], st);
+                    map[idx] = v;
+                    const unsigned long long k2 = peak_key(v, (uint32_t)idx);
+                    key = k2 > key ? k2 : key;
+                }
+            }
+        }
+        // per-angle running argmax: warp-aggregate, then one shared atomic per warp and angle
+        for (int a2 = 0; a2 < nb; ++a2) {
+            unsigned long long k2 = (my_ai == a2) ? key : 0ull;
+            k2 = warp_max_u64(k2);
+            if (lane == 0 && k2) atomicMax(&S.key[a2], k2);
+        }
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void pm_tiles_dispatch(int tx, const uint32_t *win32, int wpw, const uint32_t *tpl32, int tpw,
+                                                  int s, int nb, int RH, int RW, const uint32_t *wsum,
+                                                  const double *wden, float *maps, int max_rr, PmShared &S) {
+    switch (tx) {
+        case 8: pm_tiles<8, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
+        case 9: pm_tiles<9, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
+        case 10: pm_tiles<10, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
+        case 11: pm_tiles<11, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
+        case 12: pm_tiles<12, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
+        default: pm_tiles<13, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
+    }
+}
+
+// outputs per thread: the TX in [8,13] that wastes the fewest padded columns
+__host__ __device__ inline int pm_pick_tx(int RW) {
+    const int nwc = (RW + 3) >> 2;
+    int best = 8, best_cost = 1 << 30;
+    for (int tx = 8; tx <= 13; ++tx) {
+        const int cost = (nwc + tx - 1) / tx * tx;
+        if (cost <= best_cost) { best_cost = cost; best = tx; }
+    }
+    return best;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    __shared__ PmShared S;
+    uint32_t *win32 = reinterpret_cast<uint32_t *>(pm_smem);
+    uint32_t *tpl32 = win32 + a.win_words;
+    const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;   // nt <= PM_THREADS, chosen by the host
+    const int s = a.s, tpw = a.tpw, ab = a.ab;
+
+    // per-CTA scratch slab
+    unsigned char *slab = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
+    double *wden = reinterpret_cast<double *>(slab);
+    uint32_t *wsum = reinterpret_cast<uint32_t *>(wden + a.max_rr);
+    uint32_t *hs = wsum + a.max_rr;
+    uint32_t *hq = hs + a.max_hrw;
+    float *maps = reinterpret_cast<float *>(hq + a.max_hrw);   // (ab + 3) maps of max_rr floats
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) S.point = atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const long long pi = (long long)S.point;
+        if (pi >= a.n) break;
+        const long long pt = a.order ? (long long)a.order[pi] : pi;
+        const double c1 = a.c1[pt], r1 = a.r1[pt], c2 = a.c2fg[pt], r2 = a.r2fg[pt], brd = a.border[pt];
+        double *o = a.out + 5 * pt;
+
+        // ---- window rectangle: img2[int(r2-hws-b):int(r2+hws+b+1), int(c2-hws-b):int(c2+hws+b+1)]
+        const int hws = s / 2;
+        bool ok = isfinite(c1) && isfinite(r1) && isfinite(c2) && isfinite(r2) && isfinite(brd) &&
+                  fabs(c2) < 1e9 && fabs(r2) < 1e9 && fabs(brd) < 1e9;
+        long long y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+        if (ok) {
+            y0 = (long long)(r2 - (double)hws - brd);
+            y1 = (long long)(r2 + (double)hws + brd + 1.0);
+            x0 = (long long)(c2 - (double)hws - brd);
+            x1 = (long long)(c2 + (double)hws + brd + 1.0);
+            if (y1 > a.rows2) y1 = a.rows2;      // numpy slicing clips the far end
+            if (x1 > a.cols2) x1 = a.cols2;
+            ok = y0 >= 0 && x0 >= 0 && (y1 - y0) >= s + 1 && (x1 - x0) >= s + 1;
+        }
+        const int H = (int)(y1 - y0), W = (int)(x1 - x0);
+        const int RH = H - s + 1, RW = W - s + 1, RR = RH * RW;
+        const int wpw = pm_window_pitch_words(W);
+        if (ok) ok = RR <= a.max_rr && H * RW <= a.max_hrw && H * wpw + PM_WIN_SLACK <= a.win_words;
+        if (!ok) {
+            if (tid == 0) {
+                o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
+                if (a.status) a.status[pt] = -1;
+            }
+            continue;
+        }
+
+        // ---- 1. stage the window, word-aligned
+        {
+            const int al = (int)(x0 & 3);
+            const unsigned char *g = a.img2 + y0 * a.pitch2 + (x0 - al);
+            const int total = H * wpw;
+            for (int t = tid; t < total; t += nt) {
+                const int y = t / wpw, k = t - y * wpw;
+                const uint32_t *g32 = reinterpret_cast<const uint32_t *>(g + (long long)y * a.pitch2);
+                win32[t] = __funnelshift_r(__ldg(g32 + k), __ldg(g32 + k + 1), 8 * al);
+            }
+            if (tid == 0) { S.best_r = -INFINITY; S.best_a = -1; S.best_idx = 0; S.best_slot = -1; }
+        }
+        __syncthreads();
+
+        // ---- 2a. horizontal sliding sums over template width, every window row
+        {
+            const unsigned char *wb = reinterpret_cast<const unsigned char *>(win32);
+            const int pitchb = wpw * 4;
+            const int nseg = (RW + PM_SEG - 1) / PM_SEG;
+            for (int t = tid; t < H * nseg; t += nt) {
+                const int y = t / nseg, xs = (t - y * nseg) * PM_SEG;
+                const int xe = min(RW, xs + PM_SEG);
+                const unsigned char *rowp = wb + y * pitchb;
+                uint32_t sum = 0, sq = 0;
+                for (int j = 0; j < s; ++j) { const uint32_t v = rowp[xs + j]; sum += v; sq += v * v; }
+                for (int x = xs; x < xe; ++x) {
+                    hs[y * RW + x] = sum; hq[y * RW + x] = sq;
+                    const uint32_t va = rowp[x], vb = rowp[x + s];
+                    sum += vb - va; sq += vb * vb - va * va;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 2b. vertical sliding sums -> window sum and denominator per displacement
+        {
+            const int nseg = (RH + PM_SEG - 1) / PM_SEG;
+            for (int t = tid; t < RW * nseg; t += nt) {
+                const int sg = t / RW, x = t - sg * RW;
+                const int ys = sg * PM_SEG, ye = min(RH, ys + PM_SEG);
+                uint32_t sum = 0, sq = 0;
+                for (int i = 0; i < s; ++i) { sum += hs[(ys + i) * RW + x]; sq += hq[(ys + i) * RW + x]; }
+                for (int y = ys; y < ye; ++y) {
+                    wsum[y * RW + x] = sum;
+                    wden[y * RW + x] = window_den(sum, sq, a.inv_area);
+                    if (y + 1 < ye) {
+                        sum += hs[(y + s) * RW + x] - hs[y * RW + x];
+                        sq += hq[(y + s) * RW + x] - hq[y * RW + x];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. angle batches
+        const int A = a.n_angles;
+        const int nbatch = (A + ab - 1) / ab;
+        const int per = (A + nbatch - 1) / nbatch;
+        const int txsel = pm_pick_tx(RW);
+        bool has_zero = false;
+        for (int a0 = 0; a0 < A; a0 += per) {
+            const int nb = min(per, A - a0);
+            for (int t = tid; t < nb * s * tpw; t += nt) tpl32[t] = 0u;
+            if (tid < PM_MAX_AB) { S.tsum[tid] = 0; S.tsq[tid] = 0; S.key[tid] = 0ull; }
+            if (tid == 0) S.haszero = 0;
+            __syncthreads();
+            // gather rotated templates (get_template)
+            {
+                unsigned char *tb = reinterpret_cast<unsigned char *>(tpl32);
+                const int ss = s * s, iters = (ss + nt - 1) / nt;
+                for (int ai = 0; ai < nb; ++ai) {
+                    const double *tab = a.tab + 4 * (a0 + ai);
+                    const double cs = tab[0], sn = tab[1];
+                    const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
+                    uint32_t lsum = 0, lsq = 0; int lzero = 0;
+                    for (int it = 0; it < iters; ++it) {
+                        const int k = it * nt + tid;
+                        if (k < ss) {
+                            const int i = k / s, j = k - i * s;
+                            const uint32_t v = template_pixel(a.img1, a.rows1, a.cols1, a.pitch1, off0, off1, cs, sn, i, j, a.rot_order);
+                            tb[(ai * s + i) * tpw * 4 + j] = (unsigned char)v;
+                            lsum += v; lsq += v * v; lzero |= (v == 0);
+                        }
+                    }
+                    lsum = __reduce_add_sync(0xffffffffu, lsum);
+                    lsq = __reduce_add_sync(0xffffffffu, lsq);
+                    lzero = __any_sync(0xffffffffu, lzero);
+                    if (lane == 0) {
+                        atomicAdd(&S.tsum[ai], lsum); atomicAdd(&S.tsq[ai], lsq);
+                        if (lzero) S.haszero = 1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (S.haszero) { has_zero = true; break; }
+            if (tid < nb) {
+                S.st[tid] = templ_stats(S.tsum[tid], S.tsq[tid], a.inv_area, a.sqrt_inv_area);
+                int slot = tid;                 // tid-th slot that does not hold the best map so far
+                if (S.best_slot >= 0 && slot >= S.best_slot) ++slot;
+                S.slot[tid] = slot;
+            }
+            __syncthreads();
+            pm_tiles_dispatch<NW>(txsel, win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, a.max_rr, S);
+            __syncthreads();
+            if (tid == 0) {
+                for (int ai = 0; ai < nb; ++ai) {           // angle order, strict '>'
+                    const unsigned long long k = S.key[ai];
+                    const float v = key_f32((uint32_t)(k >> 32));
+                    if (v > S.best_r) {
+                        S.best_r = v; S.best_a = a0 + ai;
+                        S.best_idx = (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull));
+                        S.best_slot = S.slot[ai];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (has_zero || S.best_a < 0) {
+            if (tid == 0) {
+                o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
+                if (a.status) a.status[pt] = 0;
+            }
+            continue;
+        }
+
+        // ---- 4. peak statistics and bookkeeping
+        const int best_slot = S.best_slot, best_idx = S.best_idx;
+        const float *best = maps + (size_t)best_slot * a.max_rr;
+        float *tmp_a = maps + (size_t)(best_slot == 0 ? 1 : 0) * a.max_rr;
+        float *tmp_b = maps + (size_t)(ab + 1) * a.max_rr;
+        float *hes = maps + (size_t)(ab + 2) * a.max_rr;
+        const PeakStats ps = peak_statistics(best, RH, RW, best_idx, S.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, S.bs);
+        if (tid == 0) {
+            const int bi = best_idx / RW, bj = best_idx - bi * RW;
+            const double dr = (double)bi - (double)(H - s) / 2.0;
+            const double dc = (double)bj - (double)(W - s) / 2.0;
+            o[0] = c2 + dc;
+            o[1] = r2 + dr;
+            o[2] = a.angles[S.best_a];
+            o[3] = (double)ps.r;
+            o[4] = (double)ps.h;
+            if (a.status) a.status[pt] = 1;
+        }
+    }
+}
+
+inline size_t pm_scratch_bytes(int max_rr, int max_hrw, int ab) {
+    size_t b = (size_t)max_rr * 8 + (size_t)max_rr * 4 + (size_t)max_hrw * 8 + (size_t)(ab + 3) * max_rr * 4;
+    return (b + 255) & ~(size_t)255;
+}
+
+}  // namespace sid

@@ -1,0 +1,218 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against (a) the golden
+vectors of the live reference, (b) the exact CPU oracle on seeded inputs, and (c)
+size-independent properties at BASELINE.json's full sizes.  Needs a B200 (-m gpu)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+import sea_ice_drift_b200 as sid
+from sea_ice_drift_b200 import _lib, synthetic as syn, sharding
+from oracle import c_oracle as co
+from tests.helpers import variant_inputs, classify, make_exact_lookup, assert_parity
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = ["default", "one_angle", "rot_order1", "hes_smth", "raw_hes_mcc_norm", "even50_7angles",
+            "s51_b60", "s21_b9"]
+
+
+def flags(opts):
+    return _lib.flags_from_kwargs(opts["hes_norm"], opts["hes_smth"], opts["mcc_norm"])
+
+
+def assert_equals_exact_oracle(got, ref, st_got=None, st_ref=None):
+    """GPU vs the exact CPU oracle: integers and r bit-exact, h to float32 rounding."""
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref[:, 0])
+    assert np.array_equal(got[ok, :3], ref[ok, :3]), "position / angle differ from the exact oracle"
+    assert np.array_equal(got[ok, 3], ref[ok, 3]), "r differs from the exact oracle"
+    assert np.all(np.abs(got[ok, 4] - ref[ok, 4]) <= 4e-6 * (1 + np.abs(ref[ok, 4])))
+    if st_got is not None:
+        assert np.array_equal(st_got, st_ref)
+
+
+@pytest.mark.parametrize("name", VARIANTS)
+def test_golden_reference_tables(gpu_ctx, golden_points, name):
+    g = golden_points
+    pts, s, alpha0, angles, opts, ref = variant_inputs(g, name)
+    gpu_ctx.set_pair(g["img1"], g["img2"])
+    got, status = gpu_ctx.run(*pts, s, angles, alpha0, opts["rot_order"], flags(opts), want_status=True)
+    stats = classify(got, ref, make_exact_lookup(co, pts, g["img1"], g["img2"], s, alpha0, angles, opts))
+    assert_parity(stats)
+    exact, st2 = co.use_mcc_batch(*pts, g["img1"], g["img2"], s, alpha0, angles=angles, **opts)
+    assert_equals_exact_oracle(got, exact, status, st2)
+
+
+def test_golden_stage_vectors(gpu_ctx, golden_points, golden_stages):
+    g = golden_stages
+    for k, (c, r, ang, s, order) in enumerate(g["tpl_cases"]):
+        got = gpu_ctx.get_template(g["img"], c, r, ang, int(s), int(order))
+        assert np.array_equal(got, g["tpl_%d" % k]), "template case %d" % k
+    for k in range(4):
+        win, tpl, ref = g["mt_win_%d" % k], g["mt_tpl_%d" % k], g["mt_out_%d" % k]
+        got = gpu_ctx.match_template(win, tpl)
+        assert got.shape == ref.shape and got.dtype == np.float32
+        assert np.abs(got - ref).max() < 1e-5                      # cv2's own float32 noise
+        assert np.array_equal(got, co.match_template(win, tpl))    # exact oracle: bit-exact
+        for hn, hs in ((1, 0), (0, 0), (1, 1), (0, 1)):
+            h = gpu_ctx.get_hessian(ref, _lib.flags_from_kwargs(bool(hn), bool(hs), False))
+            href = g["hes_%d_%d%d" % (k, hn, hs)]
+            assert np.abs(h - href).max() <= 2e-6 * (1 + np.abs(href).max())
+    p = golden_points
+    angles = [-3, -2, -1, 0, 1, 2, 3]
+    dc, dr, a, r, h, ccm, tpl = sid.rotate_and_match(p["img1"], 210.3, 120.6, 50, p["img2"][40:190, 130:300], -3.85,
+                                                    angles=angles)
+    ref = g["ram_scalars"]
+    assert (dc, dr, a) == (ref[0], ref[1], ref[2])
+    assert abs(r - ref[3]) < 1e-4 and abs(h - ref[4]) < 1e-4
+    assert np.array_equal(tpl, g["ram_template"]) and np.abs(ccm - g["ram_result"]).max() < 1e-5
+
+
+CASES = [
+    dict(s=35, angles=[-3, 0, 3], border=(20, 50)),
+    dict(s=35, angles=[0], border=(20, 20)),
+    dict(s=35, angles=list(range(-10, 11)), border=(20, 24), n=150),
+    dict(s=35, angles=[-3, 0, 3], border=(20, 28), rot_order=1, hes_smth=True),
+    dict(s=35, angles=[-3, 3], border=(20, 22), hes_norm=False, mcc_norm=True),
+    dict(s=50, angles=[-3, 0, 3], border=(20, 30)),
+    dict(s=34, angles=[-2, 2], border=(23, 23), mcc_norm=True),
+    dict(s=51, angles=[-3, 0, 3], border=(100, 100), n=120),
+    dict(s=21, angles=[-3, 0, 3], border=(8, 14)),
+    dict(s=64, angles=[0, 5], border=(30, 40), n=200),
+    dict(s=9, angles=[0], border=(3, 6)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "s%d_a%d_b%d-%d" % (c["s"], len(c["angles"]), c["border"][0], c["border"][1]))
+def test_seeded_batches_equal_exact_oracle(gpu_ctx, case):
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=2, side=1500, grid=26)
+    img1 = img1.copy()
+    img1[690:770, 690:770] = 0                                      # NaN points
+    rng = np.random.default_rng(9)
+    n = min(case.get("n", len(c1)), len(c1))
+    brd = np.floor(rng.uniform(case["border"][0], case["border"][1] + 1, len(c1)))[:n]
+    pts = [x[:n] for x in (c1, r1, c2, r2)] + [brd]
+    pts[2][:3] = [5.0, 1490.0, 700.0]                               # windows off the left / right edge
+    opts = dict(rot_order=case.get("rot_order", 0), hes_norm=case.get("hes_norm", True),
+                hes_smth=case.get("hes_smth", False), mcc_norm=case.get("mcc_norm", False))
+    gpu_ctx.set_pair(img1, img2)
+    got, st = gpu_ctx.run(*pts, case["s"], case["angles"], 1.5, opts["rot_order"], flags(opts), want_status=True)
+    ref, st2 = co.use_mcc_batch(*pts, img1, img2, case["s"], 1.5, angles=case["angles"], **opts)
+    assert_equals_exact_oracle(got, ref, st, st2)
+    assert (st == -1).sum() >= 1 and (st == 1).sum() > n // 2
+
+
+def test_known_answer_identical_images(gpu_ctx):
+    """img2 == img1: every vector must sit at the reference's -1 px template-centre bias
+    (pmlib.py:105) with r == 1 exactly and angle 0."""
+    img = syn.speckle_image((900, 900), seed=4)
+    c, r = np.meshgrid(np.arange(100.0, 800.0, 50.0), np.arange(100.0, 800.0, 50.0))
+    c, r = c.ravel(), r.ravel()
+    gpu_ctx.set_pair(img, img)
+    out = gpu_ctx.run(c, r, c, r, np.full(c.size, 20.0), 35, [-3, 0, 3], 0.0)
+    assert np.array_equal(out[:, 0], c - 1) and np.array_equal(out[:, 1], r - 1)
+    assert np.all(out[:, 2] == 0) and np.all(out[:, 3] == 1.0) and np.all(out[:, 4] > 5)
+
+
+def test_full_size_config2_properties_and_sample(gpu_ctx):
+    """BASELINE configs[1] at full size (10400 x 10400, 200 x 200 grid, 3 angles)."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=0)
+    assert img1.shape == (10400, 10400) and len(c1) > 39000
+    gpu_ctx.set_pair(img1, img2)
+    out = gpu_ctx.run(c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
+    # determinism + independence of the processing order
+    perm = np.random.default_rng(0).permutation(len(c1))
+    out_p = gpu_ctx.run(c1[perm], r1[perm], c2[perm], r2[perm], b[perm], 35, cfg["angles"], 0.0)
+    assert np.array_equal(out[perm], out_p, equal_nan=True)
+    ok = ~np.isnan(out[:, 0])
+    assert ok.mean() > 0.99
+    assert np.all(np.abs(out[ok, 3]) <= 1.0) and np.all(np.isin(out[ok, 2], cfg["angles"]))
+    assert np.all(np.abs(out[ok, 0] - c2[ok]) <= b[ok]) and np.all(np.abs(out[ok, 1] - r2[ok]) <= b[ok])
+    tx, ty = syn.apply_affine(cfg["matrix"], c1, r1)           # known drift field, minus the -1 px bias
+    assert np.median(np.abs(out[ok, 0] - (tx[ok] - 1))) < 0.6 and np.median(np.abs(out[ok, 1] - (ty[ok] - 1))) < 0.6
+    assert np.median(out[ok, 3]) > 0.8
+    # seeded sample against the exact oracle
+    sel = np.random.default_rng(1).choice(len(c1), 1500, replace=False)
+    ref, _ = co.use_mcc_batch(c1[sel], r1[sel], c2[sel], r2[sel], b[sel], img1, img2, 35, 0.0, angles=cfg["angles"])
+    assert_equals_exact_oracle(out[sel], ref)
+
+
+def test_full_size_config4_sample(gpu_ctx):
+    """BASELINE configs[3]: img_size 51, search radius 100 (shared-memory window staging stress)."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg4", seed=0, side=4000, grid=40)
+    gpu_ctx.set_pair(img1, img2)
+    out = gpu_ctx.run(c1, r1, c2, r2, b, 51, cfg["angles"], 0.0)
+    sel = np.random.default_rng(2).choice(len(c1), 60, replace=False)
+    ref, _ = co.use_mcc_batch(c1[sel], r1[sel], c2[sel], r2[sel], b[sel], img1, img2, 51, 0.0, angles=cfg["angles"])
+    assert_equals_exact_oracle(out[sel], ref)
+
+
+def test_edge_cases_and_errors(gpu_ctx, golden_points):
+    g = golden_points
+    gpu_ctx.set_pair(g["img1"], g["img2"])
+    out = gpu_ctx.run([], [], [], [], [], 35, [0], 0.0)
+    assert out.shape == (0, 5)
+    out, st = gpu_ctx.run([245.0, 100.0, 100.0, np.nan], [160.0, 100.0, 100.0, 100.0], [245.0, 10.0, 100.0, 100.0],
+                          [160.0, 100.0, 100.0, 100.0], [20.0, 20.0, 20.0, 20.0], 35, [-3, 0, 3], 0.0, want_status=True)
+    assert st.tolist() == [0, -1, 1, -1]
+    assert np.isnan(out[[0, 1, 3]]).all() and not np.isnan(out[2]).any()
+    with pytest.raises(ValueError):
+        gpu_ctx.run([100.], [100.], [100.], [100.], [20.], 35, [0], 0.0, rot_order=3)
+    with pytest.raises(ValueError):
+        gpu_ctx.run([100.], [100.], [100.], [100.], [20.], 35, [0], 0.0, mtype=3)
+    with pytest.raises(ValueError):
+        gpu_ctx.run([100.], [100.], [100.], [100.], [20.], 300, [0], 0.0)
+    fresh = _lib.Context(0)
+    with pytest.raises(_lib.SidError):
+        fresh.run([100.], [100.], [100.], [100.], [20.], 35, [0], 0.0)      # no pair yet
+    fresh.close()
+    with pytest.raises(ValueError):
+        gpu_ctx.match_template(g["img1"][:20, :20], g["img1"][:30, :30])
+    # pitched (non-contiguous rows) input views are accepted as they are
+    view = g["img2"][40:190, 130:300]
+    assert np.array_equal(gpu_ctx.match_template(view, view[20:70, 30:80]),
+                          co.match_template(np.ascontiguousarray(view), np.ascontiguousarray(view[20:70, 30:80])))
+
+
+def test_template_matcher_plugin(golden_points):
+    import cv2
+    g = golden_points
+    win = g["img2"][100:175, 100:175]
+    base = sid.rotate_and_match(g["img1"], 140.2, 139.7, 35, win, 0.0)
+    same = sid.rotate_and_match(g["img1"], 140.2, 139.7, 35, win, 0.0, template_matcher=cv2.matchTemplate)
+    gpu = sid.rotate_and_match(g["img1"], 140.2, 139.7, 35, win, 0.0, template_matcher=sid.match_template)
+    calls = []
+
+    def custom(image, templ, method):
+        calls.append(templ.shape)
+        return cv2.matchTemplate(image, templ, method)
+    user = sid.rotate_and_match(g["img1"], 140.2, 139.7, 35, win, 0.0, template_matcher=custom)
+    assert len(calls) == 3
+    for other in (same, gpu, user):
+        assert other[:3] == base[:3] and abs(other[3] - base[3]) < 1e-5 and abs(other[4] - base[4]) < 1e-3
+    assert np.isnan(sid.rotate_and_match(g["img1"], 245.0, 160.0, 35, win, 0.0)[0])    # zero patch
+    one = sid.use_mcc(140.2, 139.7, 138.0, 137.0, 20, g["img1"], g["img2"], 35, 0.0)
+    ref = co.use_mcc_batch([140.2], [139.7], [138.0], [137.0], [20.0], g["img1"], g["img2"], 35, 0.0)[0][0]
+    assert one[:3] == tuple(ref[:3]) and one[2] in (-3, 0, 3)
+
+
+def test_pattern_matching_drop_in_end_to_end(monkeypatch):
+    from tests.test_host_api import _scene, oracle_compute
+    n1, n2, kx, ky, k2x, k2y, lon, lat, m = _scene()
+    with contextlib.redirect_stdout(io.StringIO()):
+        gpu = sid.pattern_matching(lon, lat, n1, kx, ky, n2, k2x, k2y, threads=5, angles=[-3, 0, 3])
+    monkeypatch.setattr(sharding, "use_mcc_batch_sharded",
+                        lambda *a, **k: oracle_compute(*a, **{kk: vv for kk, vv in k.items() if kk != "compute"}))
+    with contextlib.redirect_stdout(io.StringIO()):
+        cpu = sid.pattern_matching(lon, lat, n1, kx, ky, n2, k2x, k2y, threads=5, angles=[-3, 0, 3])
+    for a, b in zip(gpu, cpu):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.nanmax(np.abs(a - b)) <= 1e-4
+    drift = sid.SeaIceDrift(n1, n2)
+    lon1, lat1 = n1.transform_points(kx, ky)
+    lon2, lat2 = n2.transform_points(k2x, k2y)
+    with contextlib.redirect_stdout(io.StringIO()):
+        u = drift.get_drift_PM(lon, lat, lon1, lat1, lon2, lat2, angles=[-3, 0, 3])[0]
+    assert np.array_equal(u, gpu[0], equal_nan=True)
