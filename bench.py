@@ -243,7 +243,7 @@ def main_ours(args):
     kernel_ms = e0.elapsed_time(e1) / args.steps          # one launch of the fused kernel per step
 
     # ---- end to end through the C ABI with host buffers ("e2e")
-    ctx.set_stream(0)
+    ctx.set_stream(None)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         ctx.set_pair(img1p, img2p)

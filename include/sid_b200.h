@@ -67,8 +67,8 @@ int sid_create(sid_ctx **out, int device);
 void sid_destroy(sid_ctx *ctx);
 const char *sid_last_error(const sid_ctx *ctx);
 
-/* Run all work of this context on `cuda_stream` (a cudaStream_t passed as
- * void*; NULL = the context's own stream). */
+/* Run all work of this context on `cuda_stream` (a cudaStream_t passed as void*;
+ * NULL = the context's own stream, (void*)1 = cudaStreamLegacy, the default stream). */
 int sid_set_stream(sid_ctx *ctx, void *cuda_stream);
 int sid_synchronize(sid_ctx *ctx);
 

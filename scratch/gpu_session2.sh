@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.txt
+tail -4 gpurun_out/pytest_gpu.txt
+python scratch/time_variants.py cfg2 2>&1 | tee gpurun_out/variants_cfg2.txt
+python scratch/time_variants.py cfg1 2>&1 | tee gpurun_out/variants_cfg1.txt
+python scratch/time_variants.py cfg4 6000 120 2>&1 | tee gpurun_out/variants_cfg4.txt
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench_err.txt; echo "bench rc=$?" >> gpurun_out/bench_err.txt
+cat gpurun_out/bench.json; tail -2 gpurun_out/bench_err.txt
+ncu --set full --clock-control none --import-source on -k regex:pm_points -s 3 -c 1 -o gpurun_out/prof_pm2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1

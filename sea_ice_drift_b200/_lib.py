@@ -143,7 +143,16 @@ class Context(object):
         return int(self._lib.sid_launch_count(self._h))
 
     def set_stream(self, cuda_stream):
-        self._check(self._lib.sid_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+        """None -> the context's own stream; 0 -> CUDA's legacy default stream (what
+        torch.cuda.current_stream().cuda_stream is unless a side stream is active);
+        anything else -> that cudaStream_t."""
+        if cuda_stream is None:
+            handle = 0
+        elif int(cuda_stream) == 0:
+            handle = 1                      # cudaStreamLegacy
+        else:
+            handle = int(cuda_stream)
+        self._check(self._lib.sid_set_stream(self._h, C.c_void_p(handle)))
 
     def synchronize(self):
         self._check(self._lib.sid_synchronize(self._h))

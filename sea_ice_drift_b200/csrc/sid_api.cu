@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -44,8 +45,7 @@ struct sid_ctx {
     DevBuf pts, order, out, status, angles, scratch, counter, misc;
     void *pin = nullptr;
     size_t pin_cap = 0;
-    bool attr_set[3] = {false, false, false};
-    int attr_smem[3] = {0, 0, 0};
+    int attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -142,42 +142,81 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     a.out = d_out; a.status = d_status;
     a.max_rr = Rmax * Rmax;
     a.max_hrw = Wmax * Rmax;
-    const int wpw = pm_window_pitch_words(Wmax);
-    a.win_words = Wmax * wpw + PM_WIN_SLACK;
+    // correlation path: tensor cores (IMMA, exact u8 x u8 -> s32) unless SID_PM_PATH=dp4a
+    const char *path_env = getenv("SID_PM_PATH");
+    const bool imma = !(path_env && strcmp(path_env, "dp4a") == 0);
+    const int wpw = pm_window_pitch_words(Wmax, imma);
+    a.win_words = (Wmax + (imma ? PM_IMMA_ROW_SLACK : 0)) * wpw + PM_WIN_SLACK;
     const int nw = (s + 3) / 4;
-    int variant;                      // kernel specialisation by template width in words
+    int variant;                      // dp4a kernel specialisation by template width in words
     if (nw == 9) variant = 0; else if (nw == 13) variant = 1; else variant = 2;
-    a.tpw = variant == 2 ? (s + 15) / 16 * 4 : (nw + 3) / 4 * 4;
-    a.ab = std::min(n_angles, PM_MAX_AB);
-    size_t smem = ((size_t)a.win_words + (size_t)a.ab * s * a.tpw) * 4;
-    while (smem > (size_t)ctx->max_smem_optin && a.ab > 1) {
-        --a.ab;
-        smem = ((size_t)a.win_words + (size_t)a.ab * s * a.tpw) * 4;
+    if (imma) {
+        a.nc = (s + 7 + 31) / 32;
+        a.tpw = (32 * a.nc + 16) / 4;
+        a.tpl_off = 8;
+        a.ab = std::min(n_angles, PM_IMMA_AB);
+    } else {
+        a.nc = 0;
+        a.tpw = variant == 2 ? (s + 15) / 16 * 4 : (nw + 3) / 4 * 4;
+        a.tpl_off = 0;
+        a.ab = std::min(n_angles, PM_MAX_AB);
     }
-    if (smem > (size_t)ctx->max_smem_optin)
-        return fail(ctx, SID_EUNSUPPORTED, "search window too large for the fused kernel (border too big)");
+    // Shared memory: window + templates (+ the per-point scratch when it all fits in a third of an SM).
+    const size_t smem_cap_fast = 75 * 1024;
+    auto base_smem = [&](int ab) { return ((size_t)a.win_words + (size_t)ab * s * a.tpw) * 4; };
+    bool smem_scratch = false;
+    size_t smem = 0;
+    for (int ab = a.ab; ab >= 1 && !smem_scratch; --ab) {
+        const size_t need = base_smem(ab) + pm_scratch_bytes(a.max_rr, a.max_hrw, ab, (flags & SID_HES_SMTH) != 0);
+        // fewer resident templates only pays if it keeps all angles in <= the same number of batches
+        if (need <= smem_cap_fast && (n_angles + ab - 1) / ab == (n_angles + a.ab - 1) / a.ab) {
+            smem_scratch = true; a.ab = ab; smem = need;
+        }
+    }
+    if (getenv("SID_PM_GLOBAL_SCRATCH")) smem_scratch = false;
+    if (!smem_scratch) {
+        smem = base_smem(a.ab);
+        while (smem > (size_t)ctx->max_smem_optin && a.ab > 1) { --a.ab; smem = base_smem(a.ab); }
+        if (smem > (size_t)ctx->max_smem_optin)
+            return fail(ctx, SID_EUNSUPPORTED, "search window too large for the fused kernel (border too big)");
+    }
 
-    // CTA size: fill the CTA with thread tiles of a typical point
+    // CTA size: fill the CTA with thread tiles (dp4a) / warp tiles (IMMA) of a typical point
     const int Rt = 2 * typ_border + (Wmax - 2 * max_border) - s + 1;
-    const int tx = pm_pick_tx(Rt);
-    const int ncg = (((Rt + 3) >> 2) + tx - 1) / tx;
-    const int nbatch = (n_angles + a.ab - 1) / a.ab;
-    const int per = (n_angles + nbatch - 1) / nbatch;
-    const long long ntiles = (long long)per * ncg * Rt * 4;
     int threads = PM_THREADS;
-    double best_eff = -1.0;
-    for (int bs = 128; bs <= PM_THREADS; bs += 32) {
-        const double eff = (double)ntiles / (double)((ntiles + bs - 1) / bs * bs);
-        if (eff >= best_eff - 1e-9) { best_eff = eff; threads = bs; }
+    if (imma) {
+        const int warp_tiles = ((Rt + 15) / 16) * ((Rt + 23) / 24);
+        double best_eff = -1.0;
+        for (int w = 4; w <= PM_IMMA_THREADS / 32; ++w) {
+            const double eff = (double)warp_tiles / (double)((warp_tiles + w - 1) / w * w);
+            if (eff >= best_eff - 1e-9) { best_eff = eff; threads = 32 * w; }
+        }
+    } else {
+        const int tx = pm_pick_tx(Rt);
+        const int ncg = (((Rt + 3) >> 2) + tx - 1) / tx;
+        const int nbatch = (n_angles + a.ab - 1) / a.ab;
+        const int per = (n_angles + nbatch - 1) / nbatch;
+        const long long ntiles = (long long)per * ncg * Rt * 4;
+        double best_eff = -1.0;
+        for (int bs = 128; bs <= PM_THREADS; bs += 32) {
+            const double eff = (double)ntiles / (double)((ntiles + bs - 1) / bs * bs);
+            if (eff >= best_eff - 1e-9) { best_eff = eff; threads = bs; }
+        }
+    }
+    if (const char *e = getenv("SID_PM_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= (imma ? PM_IMMA_THREADS : PM_THREADS) && v % 32 == 0) threads = v;
     }
 
-    const void *kfn = variant == 0 ? (const void *)pm_points_kernel<9>
-                    : variant == 1 ? (const void *)pm_points_kernel<13>
-                                   : (const void *)pm_points_kernel<0>;
-    if (!ctx->attr_set[variant] || ctx->attr_smem[variant] < (int)smem) {
+    const void *ktab[8] = {(const void *)pm_points_kernel<9, false, false>, (const void *)pm_points_kernel<13, false, false>,
+                           (const void *)pm_points_kernel<0, false, false>, (const void *)pm_points_kernel<9, true, false>,
+                           (const void *)pm_points_kernel<13, true, false>, (const void *)pm_points_kernel<0, true, false>,
+                           (const void *)pm_points_kernel<0, false, true>, (const void *)pm_points_kernel<0, true, true>};
+    const int kidx = imma ? (smem_scratch ? 7 : 6) : variant + (smem_scratch ? 3 : 0);
+    const void *kfn = ktab[kidx];
+    if (ctx->attr_smem[kidx] < (int)smem) {
         CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
-        ctx->attr_set[variant] = true;
-        ctx->attr_smem[variant] = (int)std::max(smem, (size_t)49152);
+        ctx->attr_smem[kidx] = (int)std::max(smem, (size_t)49152);
     }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
@@ -186,10 +225,13 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     if (grid > n) grid = n;
     if (grid < 1) grid = 1;
 
-    a.scratch_per_cta = pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab);
-    int rc = reserve(ctx, ctx->scratch, (size_t)a.scratch_per_cta * (size_t)grid);
-    if (rc) return rc;
-    a.scratch = (unsigned char *)ctx->scratch.p;
+    a.scratch_per_cta = pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab, (flags & SID_HES_SMTH) != 0);
+    int rc = SID_OK;
+    if (!smem_scratch) {
+        rc = reserve(ctx, ctx->scratch, (size_t)a.scratch_per_cta * (size_t)grid);
+        if (rc) return rc;
+        a.scratch = (unsigned char *)ctx->scratch.p;
+    }
     rc = reserve(ctx, ctx->counter, 256);
     if (rc) return rc;
     a.counter = (unsigned int *)ctx->counter.p;

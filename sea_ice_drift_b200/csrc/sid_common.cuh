@@ -165,35 +165,63 @@ __device__ __forceinline__ float ncc_value(int64_t corr, uint32_t wsum, double w
 }
 
 // ---------------------------------------------------------------- rotated template sample
-// get_template (reference pmlib.py:89-115) for output pixel (i, j).
+// get_template (reference pmlib.py:89-115): output pixel (i, j) samples image 1 at
+//   row = (off0 + i*cos) + j*sin,   col = (off1 + i*(-sin)) + j*cos      (FP64, no FMA)
+__device__ __forceinline__ void template_coord(double off0, double off1, double cs, double sn, int i, int j,
+                                               double &row, double &col) {
+    const double di = (double)i, dj = (double)j;
+    row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), __dmul_rn(dj, sn));
+    col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), __dmul_rn(dj, cs));
+}
+// Sample at (row, col).  CHECKED: apply scipy's mode='constant' rule (outside [0, dim-1] -> 0) and
+// clamp the bilinear neighbours; unchecked when the caller knows the whole template lies >= 1 px
+// inside the image (then neither can trigger).
+template <bool CHECKED>
+__device__ __forceinline__ uint32_t template_sample(const uint8_t *__restrict__ img, int rows, int cols, int64_t pitch,
+                                                    double row, double col, int order) {
+    if (CHECKED) {
+        if (!(row >= 0.0 && row <= (double)(rows - 1) && col >= 0.0 && col <= (double)(cols - 1))) return 0;
+    }
+    if (order == 0) {
+        int ri = __double2int_rd(__dadd_rn(row, 0.5));
+        int ci = __double2int_rd(__dadd_rn(col, 0.5));
+        if (CHECKED) { ri = min(ri, rows - 1); ci = min(ci, cols - 1); }
+        return __ldg(img + (int64_t)ri * pitch + ci);
+    }
+    const double fr = floor(row), fc = floor(col);
+    const int r0 = (int)fr, c0 = (int)fc;
+    const double fy = __dsub_rn(row, fr), fx = __dsub_rn(col, fc);
+    const double wy0 = __dsub_rn(1.0, fy), wx0 = __dsub_rn(1.0, fx);
+    int r1 = r0 + 1, c1 = c0 + 1;
+    if (CHECKED) { r1 = min(r1, rows - 1); c1 = min(c1, cols - 1); }
+    const uint8_t *p0 = img + (int64_t)r0 * pitch, *p1 = img + (int64_t)r1 * pitch;
+    double t = 0.0;
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(p0 + c0), wy0), wx0));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(p0 + c1), wy0), fx));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(p1 + c0), fy), wx0));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(p1 + c1), fy), fx));
+    t = t > 0.0 ? __dadd_rn(t, 0.5) : 0.0;
+    if (t > 255.0) t = 255.0;
+    return (uint32_t)t;
+}
 __device__ __forceinline__ uint8_t template_pixel(const uint8_t *__restrict__ img, int rows, int cols, int64_t pitch,
                                                   double off0, double off1, double cs, double sn,
                                                   int i, int j, int order) {
-    const double di = (double)i, dj = (double)j;
-    const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), __dmul_rn(dj, sn));
-    const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), __dmul_rn(dj, cs));
-    if (!(row >= 0.0 && row <= (double)(rows - 1) && col >= 0.0 && col <= (double)(cols - 1))) return 0;
-    if (order == 0) {
-        long long ri = __double2ll_rd(__dadd_rn(row, 0.5));
-        long long ci = __double2ll_rd(__dadd_rn(col, 0.5));
-        if (ri > rows - 1) ri = rows - 1;
-        if (ci > cols - 1) ci = cols - 1;
-        return __ldg(img + ri * pitch + ci);
+    double row, col;
+    template_coord(off0, off1, cs, sn, i, j, row, col);
+    return (uint8_t)template_sample<true>(img, rows, cols, pitch, row, col, order);
+}
+// true when all four template corners map >= 1 px inside the image: the affine map of the
+// s x s index square is a parallelogram, so every sample is then strictly inside.
+__device__ __forceinline__ bool template_inside(int rows, int cols, double off0, double off1, double cs, double sn, int s) {
+    bool in = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double row, col;
+        template_coord(off0, off1, cs, sn, (c & 1) ? s - 1 : 0, (c & 2) ? s - 1 : 0, row, col);
+        in = in && row >= 1.0 && row <= (double)(rows - 2) && col >= 1.0 && col <= (double)(cols - 2);
     }
-    const double fr = floor(row), fc = floor(col);
-    const long long r0 = (long long)fr, c0 = (long long)fc;
-    const double fy = __dsub_rn(row, fr), fx = __dsub_rn(col, fc);
-    const double wy0 = __dsub_rn(1.0, fy), wx0 = __dsub_rn(1.0, fx);
-    const long long r1 = r0 + 1 > rows - 1 ? rows - 1 : r0 + 1;
-    const long long c1 = c0 + 1 > cols - 1 ? cols - 1 : c0 + 1;
-    double t = 0.0;
-    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r0 * pitch + c0), wy0), wx0));
-    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r0 * pitch + c1), wy0), fx));
-    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r1 * pitch + c0), fy), wx0));
-    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)__ldg(img + r1 * pitch + c1), fy), fx));
-    t = t > 0.0 ? __dadd_rn(t, 0.5) : 0.0;
-    if (t > 255.0) t = 255.0;
-    return (uint8_t)t;
+    return in;
 }
 
 // ---------------------------------------------------------------- Hessian pieces
@@ -206,6 +234,12 @@ __device__ __forceinline__ float grad_at(const float *__restrict__ line, int n, 
 }
 // gradient of the gradient along the same axis
 __device__ __forceinline__ float grad2_at(const float *__restrict__ line, int n, int stride, int i) {
+    if (i >= 2 && i <= n - 3) {          // interior: both neighbouring first derivatives are central differences
+        const float c = line[i * stride];
+        const float gp = __fmul_rn(__fsub_rn(line[(i + 2) * stride], c), 0.5f);
+        const float gm = __fmul_rn(__fsub_rn(c, line[(i - 2) * stride]), 0.5f);
+        return __fmul_rn(__fsub_rn(gp, gm), 0.5f);
+    }
     if (i == 0) return __fsub_rn(grad_at(line, n, stride, 1), grad_at(line, n, stride, 0));
     if (i == n - 1) return __fsub_rn(grad_at(line, n, stride, n - 1), grad_at(line, n, stride, n - 2));
     return __fmul_rn(__fsub_rn(grad_at(line, n, stride, i + 1), grad_at(line, n, stride, i - 1)), 0.5f);
@@ -252,15 +286,25 @@ __device__ PeakStats peak_statistics(const float *__restrict__ best, int rows, i
                                      float *__restrict__ tmp_a, float *__restrict__ tmp_b, float *__restrict__ hes,
                                      BlockScratch &bs) {
     const int tid = threadIdx.x, nt = blockDim.x, n = rows * cols;
+    const int y_first = tid / cols, x_first = tid - y_first * cols, dy = nt / cols, dx = nt - dy * cols;
     const float *src = best;
     if (flags & 2u) {               // hes_smth
-        for (int k = tid; k < n; k += nt) tmp_a[k] = gauss_at(best, rows, cols, k / cols, k % cols, 0, gw);
+        for (int k = tid, y = y_first, x = x_first; k < n; k += nt) {
+            tmp_a[k] = gauss_at(best, rows, cols, y, x, 0, gw);
+            x += dx; y += dy; if (x >= cols) { x -= cols; ++y; }
+        }
         __syncthreads();
-        for (int k = tid; k < n; k += nt) tmp_b[k] = gauss_at(tmp_a, rows, cols, k / cols, k % cols, 1, gw);
+        for (int k = tid, y = y_first, x = x_first; k < n; k += nt) {
+            tmp_b[k] = gauss_at(tmp_a, rows, cols, y, x, 1, gw);
+            x += dx; y += dy; if (x >= cols) { x -= cols; ++y; }
+        }
         __syncthreads();
         src = tmp_b;
     }
-    for (int k = tid; k < n; k += nt) hes[k] = hessian_at(src, rows, cols, k / cols, k % cols);
+    for (int k = tid, y = y_first, x = x_first; k < n; k += nt) {
+        hes[k] = hessian_at(src, rows, cols, y, x);
+        x += dx; y += dy; if (x >= cols) { x -= cols; ++y; }
+    }
     __syncthreads();
     PeakStats ps;
     ps.h = hes[peak_idx];

@@ -30,7 +30,8 @@ namespace sid {
 
 constexpr int PM_THREADS = 256;
 constexpr int PM_MAX_AB = 4;      // angles whose templates sit in shared memory together
-constexpr int PM_SEG = 16;        // outputs per sliding-sum work item
+constexpr int PM_SEG = 16;        // outputs per horizontal sliding-sum work item
+constexpr int PM_VSEG = 8;        // outputs per vertical sliding-sum work item
 constexpr int PM_WIN_SLACK = 64;  // words readable past the staged window
 
 struct PmArgs {
@@ -56,14 +57,24 @@ struct PmArgs {
     int win_words;                // capacity of the staged window (32-bit words, incl. slack)
     int tpw;                      // template row pitch in words (multiple of 4)
     int ab;                       // angles per batch
+    int tpl_off;                  // byte offset of template column 0 inside a template row (IMMA path: 8)
+    int nc;                       // IMMA path: 32-byte K chunks per template row = ceil((s + 7) / 32)
     unsigned int *counter;        // work-stealing cursor
 };
 
-__host__ __device__ inline int pm_window_pitch_words(int W) {
+__host__ __device__ inline int pm_window_pitch_words(int W, bool imma = false) {
+    if (imma) {                           // pitch == 8 (mod 16) words: the 4 rows of a half-warp's LDS.64 tile all 32 banks
+        int w = (W + 4 + 3) / 4;
+        while ((w & 15) != 8) ++w;
+        return w;
+    }
     int n16 = (W + 4 + 15) / 16;          // 16-byte units, with room for the shifted tail
     if ((n16 & 1) == 0) ++n16;            // odd multiple of 16 B -> 8 consecutive rows hit 8 distinct bank groups
     return n16 * 4;
 }
+constexpr int PM_IMMA_THREADS = 192;      // 6 warps: 3 CTAs/SM at <= 112 registers
+constexpr int PM_IMMA_AB = 3;             // angles per batch on the tensor-core path (36 accumulators per thread)
+constexpr int PM_IMMA_ROW_SLACK = 16;     // window rows readable past H (padded 16-row output blocks)
 
 // ---- correlation numerators for one thread tile -----------------------------------
 // acc[tx] += sum_i sum_jj dp4a(window word (row y+i, word q0+tx+jj, byte shift p), template word (i, jj))
@@ -123,7 +134,7 @@ struct PmShared {
     uint32_t tsum[PM_MAX_AB], tsq[PM_MAX_AB];
     int slot[PM_MAX_AB];
     int haszero;
-    unsigned int point;
+    unsigned int point, next;
     float best_r;
     int best_a, best_idx, best_slot;
 };
@@ -196,6 +207,97 @@ __device__ __forceinline__ void pm_tiles_dispatch(int tx, const uint32_t *win32,
     }
 }
 
+// ---- tensor-core path: exact u8 x u8 -> s32 correlation with mma.sync.m16n8k32 (IMMA.16832) ----------
+// For one template row i:  C[y][x] += sum_k A[y][k] * B[k][x]  with
+//   A = 16 window rows (y0+i .. y0+i+15) x 32 window columns, straight from the staged window (no im2col);
+//   B = Toeplitz band of template row i:  B[k][x] = T[i][col(k) - x], zero outside [0, s).
+// The K slots are permuted so that a thread's two A words of a row are adjacent in memory (one LDS.64) and
+// its two B words are 8 consecutive bytes of the zero-padded template row at byte (32c + 8*tig - g): three
+// aligned words and two funnel shifts.  A warp owns a 16 x 24 output tile for all NBA resident angles, so
+// every window fragment feeds NBA MMAs.
+__device__ __forceinline__ void mma_u8_16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NBA>
+__device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32, int wpw,
+                                              const uint32_t *__restrict__ tpl32, int tpw, int s, int nc,
+                                              int RH, int RW,
+                                              const uint32_t *__restrict__ wsum, const double *__restrict__ wden,
+                                              float *__restrict__ maps, int max_rr, PmShared &S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int nxg = (RW + 23) / 24;
+    const int ntiles = ((RH + 15) >> 4) * nxg;
+    const int ob = 8 + 8 * tig - g;               // byte offset of this lane's B bytes inside a padded template row
+    const int bw = ob >> 2, bsh = (ob & 3) * 8;
+    unsigned long long key[NBA];
+#pragma unroll
+    for (int a = 0; a < NBA; ++a) key[a] = 0ull;
+    for (int t = warp; t < ntiles; t += nwarps) {
+        const int yb = t / nxg, xg = t - yb * nxg;
+        const int y0 = yb * 16, x0 = xg * 24;
+        int acc[NBA][3][4];
+#pragma unroll
+        for (int a = 0; a < NBA; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[a][b][e] = 0;
+        const uint32_t *arow = win32 + (y0 + g) * wpw + (x0 >> 2) + 2 * tig;
+        const uint32_t *trow = tpl32 + bw;
+        for (int i = 0; i < s; ++i) {
+            for (int c = 0; c < nc; ++c) {
+                uint2 alo[3], ahi[3];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    alo[b] = *reinterpret_cast<const uint2 *>(arow + 8 * c + 2 * b);
+                    ahi[b] = *reinterpret_cast<const uint2 *>(arow + 8 * wpw + 8 * c + 2 * b);
+                }
+#pragma unroll
+                for (int a = 0; a < NBA; ++a) {
+                    const uint32_t *tr = trow + a * s * tpw + 8 * c;
+                    const uint32_t w0 = tr[0], w1 = tr[1], w2 = tr[2];
+                    const uint32_t b0 = __funnelshift_r(w0, w1, bsh), b1 = __funnelshift_r(w1, w2, bsh);
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) mma_u8_16832(acc[a][b], alo[b].x, ahi[b].x, alo[b].y, ahi[b].y, b0, b1);
+                }
+            }
+            arow += wpw;
+            trow += tpw;
+        }
+        // epilogue: C fragment (row g / g+8, columns 2*tig, 2*tig+1 of each 8-column block)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int y = y0 + g + 8 * h, x = x0 + 8 * b + 2 * tig + e;
+                    if (y < RH && x < RW) {
+                        const int idx = y * RW + x;
+                        const uint32_t ws = wsum[idx];
+                        const double wd = wden[idx];
+#pragma unroll
+                        for (int a = 0; a < NBA; ++a) {
+                            const float v = ncc_value((long long)acc[a][b][2 * h + e], ws, wd, S.st[a]);
+                            maps[(size_t)S.slot[a] * max_rr + idx] = v;
+                            const unsigned long long k2 = peak_key(v, (uint32_t)idx);
+                            key[a] = k2 > key[a] ? k2 : key[a];
+                        }
+                    }
+                }
+    }
+#pragma unroll
+    for (int a = 0; a < NBA; ++a) {
+        const unsigned long long k2 = warp_max_u64(key[a]);
+        if (lane == 0 && k2) atomicMax(&S.key[a], k2);
+    }
+}
+
 // outputs per thread: the TX in [8,13] that wastes the fewest padded columns
 __host__ __device__ inline int pm_pick_tx(int RW) {
     const int nwc = (RW + 3) >> 2;
@@ -207,8 +309,21 @@ __host__ __device__ inline int pm_pick_tx(int RW) {
     return best;
 }
 
-template <int NW>
-__global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a) {
+// Scratch footprint of one CTA (bytes): wden f64[rr] | wsum u32[rr] | region, where the region
+// holds the NCC maps and, before any map exists, the horizontal sums hs/hq u32[hrw] each.
+__host__ __device__ inline size_t pm_scratch_bytes(int max_rr, int max_hrw, int ab, bool smth) {
+    // maps: ab + 1 angle slots (one always keeps the best so far), the Hessian map, and a second
+    // smoothing temporary only when hes_smth is requested
+    size_t maps = (size_t)(ab + 2 + (smth ? 1 : 0)) * max_rr * 4, hsq = (size_t)max_hrw * 8;
+    size_t b = (size_t)max_rr * 12 + (maps > hsq ? maps : hsq);
+    return (b + 255) & ~(size_t)255;
+}
+
+// SMEM_SCRATCH: the per-point scratch sits in shared memory behind the templates (small search
+// windows: no L2 round trips in the statistics / epilogue / Hessian / median phases); otherwise
+// in this CTA's global slab (any window size).
+template <int NW, bool SMEM_SCRATCH, bool IMMA>
+__global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_points_kernel(const PmArgs a) {
     extern __shared__ __align__(16) unsigned char pm_smem[];
     __shared__ PmShared S;
     uint32_t *win32 = reinterpret_cast<uint32_t *>(pm_smem);
@@ -216,17 +331,22 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
     const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;   // nt <= PM_THREADS, chosen by the host
     const int s = a.s, tpw = a.tpw, ab = a.ab;
 
-    // per-CTA scratch slab
-    unsigned char *slab = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
+    unsigned char *slab;
+    if constexpr (SMEM_SCRATCH) slab = reinterpret_cast<unsigned char *>(tpl32 + ab * s * tpw);
+    else slab = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
     double *wden = reinterpret_cast<double *>(slab);
     uint32_t *wsum = reinterpret_cast<uint32_t *>(wden + a.max_rr);
-    uint32_t *hs = wsum + a.max_rr;
+    float *maps = reinterpret_cast<float *>(wsum + a.max_rr);   // (ab + 3) maps of max_rr floats
+    uint32_t *hs = reinterpret_cast<uint32_t *>(maps);          // aliases the maps: dead before the first map is written
     uint32_t *hq = hs + a.max_hrw;
-    float *maps = reinterpret_cast<float *>(hq + a.max_hrw);   // (ab + 3) maps of max_rr floats
 
+    if (tid == 0) S.next = atomicAdd(a.counter, 1u);
     for (;;) {
         __syncthreads();
-        if (tid == 0) S.point = atomicAdd(a.counter, 1u);
+        if (tid == 0) {
+            S.point = S.next;
+            if ((long long)S.point < a.n) S.next = atomicAdd(a.counter, 1u);   // prefetch the next work item
+        }
         __syncthreads();
         const long long pi = (long long)S.point;
         if (pi >= a.n) break;
@@ -250,8 +370,9 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
         }
         const int H = (int)(y1 - y0), W = (int)(x1 - x0);
         const int RH = H - s + 1, RW = W - s + 1, RR = RH * RW;
-        const int wpw = pm_window_pitch_words(W);
-        if (ok) ok = RR <= a.max_rr && H * RW <= a.max_hrw && H * wpw + PM_WIN_SLACK <= a.win_words;
+        const int wpw = pm_window_pitch_words(W, IMMA);
+        if (ok) ok = RR <= a.max_rr && H * RW <= a.max_hrw &&
+                     (H + (IMMA ? PM_IMMA_ROW_SLACK : 0)) * wpw + PM_WIN_SLACK <= a.win_words;
         if (!ok) {
             if (tid == 0) {
                 o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
@@ -260,15 +381,29 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
             continue;
         }
 
-        // ---- 1. stage the window, word-aligned
+        // ---- 1. stage the window, word-aligned (4 independent load pairs in flight per thread)
         {
             const int al = (int)(x0 & 3);
             const unsigned char *g = a.img2 + y0 * a.pitch2 + (x0 - al);
             const int total = H * wpw;
-            for (int t = tid; t < total; t += nt) {
-                const int y = t / wpw, k = t - y * wpw;
-                const uint32_t *g32 = reinterpret_cast<const uint32_t *>(g + (long long)y * a.pitch2);
-                win32[t] = __funnelshift_r(__ldg(g32 + k), __ldg(g32 + k + 1), 8 * al);
+            const int dy = nt / wpw, dk = nt - dy * wpw;              // (row, word) step of one CTA stride
+            int y = tid / wpw, k = tid - y * wpw;
+            for (int base = 0; base < total; base += 4 * nt) {
+                uint32_t lo[4], hi[4];
+                int dst[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    dst[u] = (y < H) ? y * wpw + k : -1;
+                    if (y < H) {
+                        const uint32_t *g32 = reinterpret_cast<const uint32_t *>(g + (long long)y * a.pitch2);
+                        lo[u] = __ldg(g32 + k); hi[u] = __ldg(g32 + k + 1);
+                    }
+                    k += dk; y += dy;
+                    if (k >= wpw) { k -= wpw; ++y; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (dst[u] >= 0) win32[dst[u]] = __funnelshift_r(lo[u], hi[u], 8 * al);
             }
             if (tid == 0) { S.best_r = -INFINITY; S.best_a = -1; S.best_idx = 0; S.best_slot = -1; }
         }
@@ -295,11 +430,12 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
         __syncthreads();
         // ---- 2b. vertical sliding sums -> window sum and denominator per displacement
         {
-            const int nseg = (RH + PM_SEG - 1) / PM_SEG;
+            const int nseg = (RH + PM_VSEG - 1) / PM_VSEG;
             for (int t = tid; t < RW * nseg; t += nt) {
                 const int sg = t / RW, x = t - sg * RW;
-                const int ys = sg * PM_SEG, ye = min(RH, ys + PM_SEG);
+                const int ys = sg * PM_VSEG, ye = min(RH, ys + PM_VSEG);
                 uint32_t sum = 0, sq = 0;
+#pragma unroll 5
                 for (int i = 0; i < s; ++i) { sum += hs[(ys + i) * RW + x]; sq += hq[(ys + i) * RW + x]; }
                 for (int y = ys; y < ye; ++y) {
                     wsum[y * RW + x] = sum;
@@ -311,7 +447,7 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
                 }
             }
         }
-        __syncthreads();
+        // (the barrier after the template gather below also orders these writes before their first use)
 
         // ---- 3. angle batches
         const int A = a.n_angles;
@@ -325,22 +461,43 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
             if (tid < PM_MAX_AB) { S.tsum[tid] = 0; S.tsq[tid] = 0; S.key[tid] = 0ull; }
             if (tid == 0) S.haszero = 0;
             __syncthreads();
-            // gather rotated templates (get_template)
+            // gather rotated templates (get_template): thread = (column j, row group); the j terms of the
+            // coordinates are hoisted, and a corner test removes the per-pixel bounds checks
             {
                 unsigned char *tb = reinterpret_cast<unsigned char *>(tpl32);
-                const int ss = s * s, iters = (ss + nt - 1) / nt;
+                const int rows_per_pass = nt / s;                    // >= 1 since s <= 128 <= nt
+                const int gi = tid / s, gj = tid - gi * s;
+                const bool active = gi < rows_per_pass;
+                const double dj = (double)gj;
                 for (int ai = 0; ai < nb; ++ai) {
                     const double *tab = a.tab + 4 * (a0 + ai);
                     const double cs = tab[0], sn = tab[1];
                     const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
+                    const bool inside = template_inside(a.rows1, a.cols1, off0, off1, cs, sn, s);
+                    const double jsn = __dmul_rn(dj, sn), jcs = __dmul_rn(dj, cs);
+                    unsigned char *tdst = tb + (size_t)ai * s * tpw * 4 + a.tpl_off + gj;
                     uint32_t lsum = 0, lsq = 0; int lzero = 0;
-                    for (int it = 0; it < iters; ++it) {
-                        const int k = it * nt + tid;
-                        if (k < ss) {
-                            const int i = k / s, j = k - i * s;
-                            const uint32_t v = template_pixel(a.img1, a.rows1, a.cols1, a.pitch1, off0, off1, cs, sn, i, j, a.rot_order);
-                            tb[(ai * s + i) * tpw * 4 + j] = (unsigned char)v;
-                            lsum += v; lsq += v * v; lzero |= (v == 0);
+                    for (int i0 = 0; i0 < s; i0 += 4 * rows_per_pass) {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * rows_per_pass + gi;
+                            v[u] = 1u;
+                            if (active && i < s) {
+                                const double di = (double)i;
+                                const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), jsn);
+                                const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), jcs);
+                                v[u] = inside ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order)
+                                              : template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * rows_per_pass + gi;
+                            if (active && i < s) {
+                                tdst[i * tpw * 4] = (unsigned char)v[u];
+                                lsum += v[u]; lsq += v[u] * v[u]; lzero |= (v[u] == 0);
+                            }
                         }
                     }
                     lsum = __reduce_add_sync(0xffffffffu, lsum);
@@ -354,6 +511,7 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
             }
             __syncthreads();
             if (S.haszero) { has_zero = true; break; }
+            // every thread derives the template statistics it needs; thread < nb publishes slot + stats
             if (tid < nb) {
                 S.st[tid] = templ_stats(S.tsum[tid], S.tsq[tid], a.inv_area, a.sqrt_inv_area);
                 int slot = tid;                 // tid-th slot that does not hold the best map so far
@@ -361,7 +519,13 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
                 S.slot[tid] = slot;
             }
             __syncthreads();
-            pm_tiles_dispatch<NW>(txsel, win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, a.max_rr, S);
+            if constexpr (IMMA) {
+                if (nb == 1) pm_tiles_imma<1>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+                else if (nb == 2) pm_tiles_imma<2>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+                else pm_tiles_imma<3>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+            } else {
+                pm_tiles_dispatch<NW>(txsel, win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, a.max_rr, S);
+            }
             __syncthreads();
             if (tid == 0) {
                 for (int ai = 0; ai < nb; ++ai) {           // angle order, strict '>'
@@ -388,8 +552,8 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
         const int best_slot = S.best_slot, best_idx = S.best_idx;
         const float *best = maps + (size_t)best_slot * a.max_rr;
         float *tmp_a = maps + (size_t)(best_slot == 0 ? 1 : 0) * a.max_rr;
-        float *tmp_b = maps + (size_t)(ab + 1) * a.max_rr;
-        float *hes = maps + (size_t)(ab + 2) * a.max_rr;
+        float *hes = maps + (size_t)(ab + 1) * a.max_rr;
+        float *tmp_b = maps + (size_t)(ab + 2) * a.max_rr;      // only allocated (and touched) with hes_smth
         const PeakStats ps = peak_statistics(best, RH, RW, best_idx, S.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, S.bs);
         if (tid == 0) {
             const int bi = best_idx / RW, bj = best_idx - bi * RW;
@@ -405,9 +569,5 @@ __global__ void __launch_bounds__(PM_THREADS, 3) pm_points_kernel(const PmArgs a
     }
 }
 
-inline size_t pm_scratch_bytes(int max_rr, int max_hrw, int ab) {
-    size_t b = (size_t)max_rr * 8 + (size_t)max_rr * 4 + (size_t)max_hrw * 8 + (size_t)(ab + 3) * max_rr * 4;
-    return (b + 255) & ~(size_t)255;
-}
 
 }  // namespace sid
