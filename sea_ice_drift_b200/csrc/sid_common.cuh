@@ -224,6 +224,15 @@ __device__ __forceinline__ bool template_inside(int rows, int cols, double off0,
     return in;
 }
 
+// same test, one corner per lane (lanes 0..3), result uniform over the warp
+__device__ __forceinline__ bool template_inside_warp(int rows, int cols, double off0, double off1, double cs, double sn, int s) {
+    const int c = threadIdx.x & 3;
+    double row, col;
+    template_coord(off0, off1, cs, sn, (c & 1) ? s - 1 : 0, (c & 2) ? s - 1 : 0, row, col);
+    const bool in = row >= 1.0 && row <= (double)(rows - 2) && col >= 1.0 && col <= (double)(cols - 2);
+    return __all_sync(0xffffffffu, in);
+}
+
 // ---------------------------------------------------------------- Hessian pieces
 // np.gradient along one axis (unit spacing, edge_order=1) at position `i` of a line
 // of `n` float32 samples spaced `stride` apart.
@@ -301,9 +310,34 @@ __device__ PeakStats peak_statistics(const float *__restrict__ best, int rows, i
         __syncthreads();
         src = tmp_b;
     }
-    for (int k = tid, y = y_first, x = x_first; k < n; k += nt) {
-        hes[k] = hessian_at(src, rows, cols, y, x);
-        x += dx; y += dy; if (x >= cols) { x -= cols; ++y; }
+    if (rows >= 5 && cols >= 5) {
+        // interior (2 <= y < rows-2, 2 <= x < cols-2): branch-free 5-point stencils, same rounding sequence as
+        // np.gradient(np.gradient(.)) away from the edges
+        const int iw = cols - 4, ni = (rows - 4) * iw;
+        const int iy_first = tid / iw, ix_first = tid - iy_first * iw, idy = nt / iw, idx = nt - idy * iw;
+        for (int k = tid, y = iy_first, x = ix_first; k < ni; k += nt) {
+            const float *p = src + (size_t)(y + 2) * cols + (x + 2);
+            const float c = p[0];
+            const float gxp = __fmul_rn(__fsub_rn(p[2], c), 0.5f), gxm = __fmul_rn(__fsub_rn(c, p[-2]), 0.5f);
+            const float gyp = __fmul_rn(__fsub_rn(p[2 * cols], c), 0.5f), gym = __fmul_rn(__fsub_rn(c, p[-2 * cols]), 0.5f);
+            const double a2 = (double)__fmul_rn(__fsub_rn(gxp, gxm), 0.5f), b2 = (double)__fmul_rn(__fsub_rn(gyp, gym), 0.5f);
+            hes[(size_t)(y + 2) * cols + (x + 2)] =
+                __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(a2, a2), __dmul_rn(b2, b2))));
+            x += idx; y += idy; if (x >= iw) { x -= iw; ++y; }
+        }
+        // border frame: two rows top and bottom, two columns left and right
+        const int nb = 4 * cols + 4 * (rows - 4);
+        for (int k = tid; k < nb; k += nt) {
+            int y, x;
+            if (k < 4 * cols) { const int r = k / cols; x = k - r * cols; y = r < 2 ? r : rows - 4 + r; }
+            else { const int q = k - 4 * cols, r = q >> 2, cidx = q & 3; y = r + 2; x = cidx < 2 ? cidx : cols - 4 + cidx; }
+            hes[(size_t)y * cols + x] = hessian_at(src, rows, cols, y, x);
+        }
+    } else {
+        for (int k = tid, y = y_first, x = x_first; k < n; k += nt) {
+            hes[k] = hessian_at(src, rows, cols, y, x);
+            x += dx; y += dy; if (x >= cols) { x -= cols; ++y; }
+        }
     }
     __syncthreads();
     PeakStats ps;

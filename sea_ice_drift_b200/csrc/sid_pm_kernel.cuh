@@ -222,9 +222,9 @@ __device__ __forceinline__ void mma_u8_16832(int (&c)[4], uint32_t a0, uint32_t 
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int NBA>
+template <int NBA, int NC>   // NC > 0: compile-time number of 32-byte K chunks (2 covers img_size <= 57)
 __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32, int wpw,
-                                              const uint32_t *__restrict__ tpl32, int tpw, int s, int nc,
+                                              const uint32_t *__restrict__ tpl32, int tpw, int s, int nc_rt,
                                               int RH, int RW,
                                               const uint32_t *__restrict__ wsum, const double *__restrict__ wden,
                                               float *__restrict__ maps, int max_rr, PmShared &S) {
@@ -249,24 +249,33 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
                 for (int e = 0; e < 4; ++e) acc[a][b][e] = 0;
         const uint32_t *arow = win32 + (y0 + g) * wpw + (x0 >> 2) + 2 * tig;
         const uint32_t *trow = tpl32 + bw;
+        const uint32_t *arow8 = arow + 8 * wpw;
+        const int nc = NC > 0 ? NC : nc_rt;
+        const int tstride = s * tpw;
         for (int i = 0; i < s; ++i) {
+#pragma unroll
             for (int c = 0; c < nc; ++c) {
-                uint2 alo[3], ahi[3];
+                // the four fragment words are loaded as scalars so that each lands directly in its
+                // operand register (a0..a3 must be consecutive; paired 64-bit loads would need moves)
+                uint32_t af[3][4];
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
-                    alo[b] = *reinterpret_cast<const uint2 *>(arow + 8 * c + 2 * b);
-                    ahi[b] = *reinterpret_cast<const uint2 *>(arow + 8 * wpw + 8 * c + 2 * b);
+                    af[b][0] = arow[8 * c + 2 * b];
+                    af[b][1] = arow8[8 * c + 2 * b];
+                    af[b][2] = arow[8 * c + 2 * b + 1];
+                    af[b][3] = arow8[8 * c + 2 * b + 1];
                 }
 #pragma unroll
                 for (int a = 0; a < NBA; ++a) {
-                    const uint32_t *tr = trow + a * s * tpw + 8 * c;
+                    const uint32_t *tr = trow + a * tstride + 8 * c;
                     const uint32_t w0 = tr[0], w1 = tr[1], w2 = tr[2];
                     const uint32_t b0 = __funnelshift_r(w0, w1, bsh), b1 = __funnelshift_r(w1, w2, bsh);
 #pragma unroll
-                    for (int b = 0; b < 3; ++b) mma_u8_16832(acc[a][b], alo[b].x, ahi[b].x, alo[b].y, ahi[b].y, b0, b1);
+                    for (int b = 0; b < 3; ++b) mma_u8_16832(acc[a][b], af[b][0], af[b][1], af[b][2], af[b][3], b0, b1);
                 }
             }
             arow += wpw;
+            arow8 += wpw;
             trow += tpw;
         }
         // epilogue: C fragment (row g / g+8, columns 2*tig, 2*tig+1 of each 8-column block)
@@ -381,29 +390,27 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
             continue;
         }
 
-        // ---- 1. stage the window, word-aligned (4 independent load pairs in flight per thread)
+        // ---- 1. stage the window, word-aligned: one warp per row, each lane loads one aligned word and
+        //         takes its right neighbour by shuffle; two rows in flight per warp
         {
-            const int al = (int)(x0 & 3);
-            const unsigned char *g = a.img2 + y0 * a.pitch2 + (x0 - al);
-            const int total = H * wpw;
-            const int dy = nt / wpw, dk = nt - dy * wpw;              // (row, word) step of one CTA stride
-            int y = tid / wpw, k = tid - y * wpw;
-            for (int base = 0; base < total; base += 4 * nt) {
-                uint32_t lo[4], hi[4];
-                int dst[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    dst[u] = (y < H) ? y * wpw + k : -1;
-                    if (y < H) {
-                        const uint32_t *g32 = reinterpret_cast<const uint32_t *>(g + (long long)y * a.pitch2);
-                        lo[u] = __ldg(g32 + k); hi[u] = __ldg(g32 + k + 1);
+            const int al8 = 8 * (int)(x0 & 3);
+            const unsigned char *g = a.img2 + y0 * a.pitch2 + (x0 - (x0 & 3));
+            const int warp = tid >> 5, nwarps = nt >> 5;
+            for (int kb = 0; kb < wpw; kb += 31) {                  // 31 output words per pass (lane 31 only feeds lane 30)
+                const int k = kb + lane;
+                const bool in_row = k <= wpw;                        // word wpw is read for the last shift only
+                for (int y = warp; y < H; y += 2 * nwarps) {
+                    const int yb = y + nwarps;
+                    const uint32_t *ga = reinterpret_cast<const uint32_t *>(g + (long long)y * a.pitch2);
+                    const uint32_t *gb = reinterpret_cast<const uint32_t *>(g + (long long)yb * a.pitch2);
+                    uint32_t wa = 0, wb = 0;
+                    if (in_row) { wa = __ldg(ga + k); if (yb < H) wb = __ldg(gb + k); }
+                    const uint32_t na = __shfl_down_sync(0xffffffffu, wa, 1), nb2 = __shfl_down_sync(0xffffffffu, wb, 1);
+                    if (lane < 31 && k < wpw) {
+                        win32[y * wpw + k] = __funnelshift_r(wa, na, al8);
+                        if (yb < H) win32[yb * wpw + k] = __funnelshift_r(wb, nb2, al8);
                     }
-                    k += dk; y += dy;
-                    if (k >= wpw) { k -= wpw; ++y; }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (dst[u] >= 0) win32[dst[u]] = __funnelshift_r(lo[u], hi[u], 8 * al);
             }
             if (tid == 0) { S.best_r = -INFINITY; S.best_a = -1; S.best_idx = 0; S.best_slot = -1; }
         }
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
                     const double *tab = a.tab + 4 * (a0 + ai);
                     const double cs = tab[0], sn = tab[1];
                     const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
-                    const bool inside = template_inside(a.rows1, a.cols1, off0, off1, cs, sn, s);
+                    const bool inside = template_inside_warp(a.rows1, a.cols1, off0, off1, cs, sn, s);
                     const double jsn = __dmul_rn(dj, sn), jcs = __dmul_rn(dj, cs);
                     unsigned char *tdst = tb + (size_t)ai * s * tpw * 4 + a.tpl_off + gj;
                     uint32_t lsum = 0, lsq = 0; int lzero = 0;
@@ -520,9 +527,15 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
             }
             __syncthreads();
             if constexpr (IMMA) {
-                if (nb == 1) pm_tiles_imma<1>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
-                else if (nb == 2) pm_tiles_imma<2>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
-                else pm_tiles_imma<3>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+                if (a.nc == 2) {
+                    if (nb == 1) pm_tiles_imma<1, 2>(win32, wpw, tpl32, tpw, s, 2, RH, RW, wsum, wden, maps, a.max_rr, S);
+                    else if (nb == 2) pm_tiles_imma<2, 2>(win32, wpw, tpl32, tpw, s, 2, RH, RW, wsum, wden, maps, a.max_rr, S);
+                    else pm_tiles_imma<3, 2>(win32, wpw, tpl32, tpw, s, 2, RH, RW, wsum, wden, maps, a.max_rr, S);
+                } else {
+                    if (nb == 1) pm_tiles_imma<1, 0>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+                    else if (nb == 2) pm_tiles_imma<2, 0>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+                    else pm_tiles_imma<3, 0>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+                }
             } else {
                 pm_tiles_dispatch<NW>(txsel, win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, a.max_rr, S);
             }
