@@ -8,7 +8,7 @@ rotational drift, 200 x 200 PM grid, img_size 35, angles [-3, 0, 3]).
 One step = one pass of the hot path over the whole PM grid of one image pair.
   value   : whole-job vectors/s with the pair and the point arrays already resident in HBM
             (device-timed with CUDA events on the launching stream, max over ranks).
-  e2e     : the same metric through the C-ABI call a user makes (sid_set_pair + sid_run) with
+  e2e     : the same metric through the C-ABI call a user makes (sid_run_pair) with
             HOST buffers: pinned-host -> device copy of the image pair and the point arrays and
             the device -> host read of the result table are inside the timed region.
   roofline: algorithmic FLOPs (sum over points and angles of 2 s^2 R^2) per launch
@@ -246,13 +246,11 @@ def main_ours(args):
     ctx.set_stream(None)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        ctx.set_pair(img1p, img2p)
-        host_out = ctx.run(c1, r1, c2, r2, b, s, angles, 0.0)
+        host_out = ctx.run_pair(img1p, img2p, c1, r1, c2, r2, b, s, angles, 0.0)
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.set_pair(img1p, img2p)
-        host_out = ctx.run(c1, r1, c2, r2, b, s, angles, 0.0)
+        host_out = ctx.run_pair(img1p, img2p, c1, r1, c2, r2, b, s, angles, 0.0)
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_points * e2e_steps / dt_e2e
     h2d = int(img1.nbytes + img2.nbytes + n * 5 * 8 + n * 4 + len(angles) * 5 * 8)
@@ -313,7 +311,8 @@ def main_ours(args):
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": 1e3 * dt_e2e / e2e_steps,
-                        "call": "sid_set_pair + sid_run (pinned host image pair, host point arrays, host result table)"},
+                        "call": "sid_run_pair: pinned host image pair + host point arrays in, host result table out; "
+                                "upload in row bands overlapped with the fused kernel"},
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
     ctx.close()
     if world > 1:

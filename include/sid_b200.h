@@ -4,7 +4,8 @@
  * Drop-in boundary for nansencenter/sea_ice_drift v0.7.1 (paths below are under
  * the reference tree, sea_ice_drift/):
  *
- *   sid_run / sid_run_device   replace the per-point loop of pattern_matching,
+ *   sid_run / sid_run_pair / sid_run_device
+ *                              replace the per-point loop of pattern_matching,
  *                              pmlib.py:430-448 (_init_pool + Pool.map(use_mcc_mp)),
  *                              i.e. use_mcc (pmlib.py:176-212) for every grid point.
  *                              Argument order mirrors _init_pool's tuple (pmlib.py:438).
@@ -95,6 +96,21 @@ int sid_run(sid_ctx *ctx, int64_t n,
             int img_size, int n_angles, const double *angles, const double *angle_tab,
             int rot_order, unsigned flags, int mtype,
             double *out, int *status);
+
+/* sid_set_pair + sid_run in ONE call, with the host-to-device copy of the image pair overlapped
+ * with the computation: the pair is uploaded in row bands on a second stream and the points are
+ * processed band by band as soon as every image row they touch has arrived.  Results are
+ * identical to sid_set_pair followed by sid_run; the pair stays resident afterwards.  Use pinned
+ * (page-locked) host images for the overlap to take effect. */
+int sid_run_pair(sid_ctx *ctx,
+                 const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
+                 const uint8_t *img2, int rows2, int cols2, int64_t pitch2,
+                 int64_t n,
+                 const double *c1, const double *r1,
+                 const double *c2fg, const double *r2fg, const double *border,
+                 int img_size, int n_angles, const double *angles, const double *angle_tab,
+                 int rot_order, unsigned flags, int mtype,
+                 double *out, int *status);
 
 /* Same with DEVICE pointers for the point arrays and outputs; asynchronous on
  * the context's stream (no host synchronisation).  `max_border` must bound

@@ -22,7 +22,7 @@ SID_HES_NORM, SID_HES_SMTH, SID_MCC_NORM = 1, 2, 4
 
 EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
-    "sid_set_pair", "sid_set_pair_device", "sid_run", "sid_run_device", "sid_launch_count",
+    "sid_set_pair", "sid_set_pair_device", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count",
     "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian",
 ]
 
@@ -58,6 +58,8 @@ def load_library():
         lib.sid_set_pair.argtypes = pair
         lib.sid_set_pair_device.argtypes = pair
         lib.sid_run.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + \
+            [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
+        lib.sid_run_pair.argtypes = pair + [C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
         lib.sid_run_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
@@ -184,6 +186,26 @@ class Context(object):
         self._check(self._lib.sid_run(
             self._h, n, *[a.ctypes.data for a in arrs], int(img_size), len(ang), ang.ctypes.data,
             tab.ctypes.data, int(rot_order), int(flags), int(mtype), out.ctypes.data, status.ctypes.data))
+        return (out, status) if want_status else out
+
+    def run_pair(self, img1, img2, c1, r1, c2fg, r2fg, border, img_size, angles, alpha0, rot_order=0,
+                 flags=SID_HES_NORM, mtype=SID_TM_CCOEFF_NORMED, want_status=False):
+        """Upload the pair and match all points in one call, copy overlapped with compute."""
+        img1, img2 = as_u8_image(img1), as_u8_image(img2)
+        arrs = [np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64) for x in (c1, r1, c2fg, r2fg, border)]
+        n = arrs[0].size
+        if any(a.size != n for a in arrs):
+            raise ValueError("point arrays must have equal length")
+        ang = np.ascontiguousarray(np.asarray(angles, dtype=np.float64))
+        tab = angle_table(angles, alpha0, img_size)
+        out = np.full((n, 5), np.nan, dtype=np.float64)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.sid_run_pair(
+            self._h, img1.ctypes.data, img1.shape[0], img1.shape[1], img1.strides[0],
+            img2.ctypes.data, img2.shape[0], img2.shape[1], img2.strides[0],
+            n, *[a.ctypes.data for a in arrs], int(img_size), len(ang), ang.ctypes.data,
+            tab.ctypes.data, int(rot_order), int(flags), int(mtype), out.ctypes.data, status.ctypes.data))
+        self._pair_key = None
         return (out, status) if want_status else out
 
     def run_device(self, n, d_c1, d_r1, d_c2fg, d_r2fg, d_border, max_border, img_size, angles, alpha0,

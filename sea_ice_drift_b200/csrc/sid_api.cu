@@ -34,6 +34,8 @@ struct sid_ctx {
     int max_smem_optin = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // image upload, overlapped with compute (sid_run_pair)
+    cudaEvent_t band_event[17] = {};
     std::string err;
     long long launches = 0;
     // resident image pair (padded pitch, 16-byte multiple)
@@ -279,6 +281,10 @@ void sid_destroy(sid_ctx *ctx) {
                       &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->copy_stream) {
+        cudaStreamDestroy(ctx->copy_stream);
+        for (cudaEvent_t e : ctx->band_event) if (e) cudaEventDestroy(e);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -338,35 +344,78 @@ static int upload_angles(sid_ctx *ctx, int n_angles, const double *angles, const
     return SID_OK;
 }
 
-int sid_run(sid_ctx *ctx, int64_t n, const double *c1, const double *r1, const double *c2fg,
-            const double *r2fg, const double *border, int img_size, int n_angles, const double *angles,
-            const double *angle_tab, int rot_order, unsigned flags, int mtype, double *out, int *status) {
+namespace {
+
+struct HostPair {
+    const uint8_t *img1, *img2;
+    int rows1, cols1, rows2, cols2;
+    long long pitch1, pitch2;
+};
+
+constexpr int MAX_BANDS = 16;
+
+// Body of sid_run and sid_run_pair.  With `pair` the images are uploaded in row bands on a second
+// stream while the fused kernel already works on the points whose windows and templates lie
+// entirely inside the bands that have arrived (PCIe copy overlapped with compute).
+int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, const double *r1, const double *c2fg,
+             const double *r2fg, const double *border, int img_size, int n_angles, const double *angles,
+             const double *angle_tab, int rot_order, unsigned flags, int mtype, double *out, int *status) {
     int rc = check_common(ctx, img_size, n_angles, angle_tab, rot_order, mtype);
     if (rc) return rc;
-    if (!ctx->have_pair) return fail(ctx, SID_ENOPAIR, "sid_set_pair has not been called");
+    if (!pair && !ctx->have_pair) return fail(ctx, SID_ENOPAIR, "sid_set_pair has not been called");
     if (n < 0 || (n > 0 && (!c1 || !r1 || !c2fg || !r2fg || !border || !out)) || !angles)
         return fail(ctx, SID_EINVAL, "null point array");
-    if (n == 0) return SID_OK;
     if (n > 0x7fffffffLL) return fail(ctx, SID_EINVAL, "too many points");
     CU(cudaSetDevice(ctx->device));
+    if (pair) {
+        if (!pair->img1 || !pair->img2 || pair->rows1 <= 0 || pair->cols1 <= 0 || pair->rows2 <= 0 || pair->cols2 <= 0 ||
+            pair->pitch1 < pair->cols1 || pair->pitch2 < pair->cols2)
+            return fail(ctx, SID_EINVAL, "bad image arguments");
+        if (n == 0) return sid_set_pair(ctx, pair->img1, pair->rows1, pair->cols1, pair->pitch1, pair->img2, pair->rows2,
+                                        pair->cols2, pair->pitch2);
+    }
+    if (n == 0) return SID_OK;
 
-    // borders: bound and processing order (largest window first, counting sort)
+    // ---- bands (upload granularity); a single band means "everything is already resident"
+    const int rows1 = pair ? pair->rows1 : ctx->rows1, rows2 = pair ? pair->rows2 : ctx->rows2;
+    const int max_rows = std::max(rows1, rows2);
+    int nbands = 1;
+    if (pair) nbands = std::max(1, std::min(8, max_rows / 512));     // 8 bands measured best (more = more launch tails)
+    if (pair) if (const char *e = getenv("SID_BANDS")) nbands = std::max(1, std::min(MAX_BANDS, atoi(e)));
+    const int band_rows = (max_rows + nbands - 1) / nbands;
+
+    // ---- borders: bound, typical value, and the processing order: band of the last image row a point
+    //      touches first, then largest window first (counting sort on the combined key)
     int max_border = 0;
-    std::vector<int> ib((size_t)n);
+    std::vector<int> ib((size_t)n), band((size_t)n, 0);
+    const double ext = 0.5 * std::sqrt(2.0) * (img_size + 2) + 3.0;      // template reach around (c1, r1) incl. rounding
+    const int hws = img_size / 2;
     for (int64_t i = 0; i < n; ++i) {
         const double b = border[i];
         int v = 0;
         if (std::isfinite(b) && b >= 0.0 && b < 4096.0) v = (int)b;
         ib[(size_t)i] = v;
         max_border = std::max(max_border, v);
+        if (nbands > 1) {
+            double need = 0.0;
+            if (std::isfinite(r1[i]) && std::isfinite(r2fg[i])) need = std::max(r1[i] + ext, r2fg[i] + hws + v + 2.0);
+            int k = need <= 0.0 ? 0 : (int)std::min((double)(nbands - 1), need / band_rows);
+            band[(size_t)i] = k;
+        }
     }
-    std::vector<int> hist((size_t)max_border + 2, 0);
-    for (int64_t i = 0; i < n; ++i) ++hist[(size_t)(max_border - ib[(size_t)i]) + 1];
+    const size_t nkeys = (size_t)nbands * (size_t)(max_border + 1);
+    std::vector<int> hist(nkeys + 1, 0);
+    auto key_of = [&](int64_t i) { return (size_t)band[(size_t)i] * (size_t)(max_border + 1) + (size_t)(max_border - ib[(size_t)i]); };
+    for (int64_t i = 0; i < n; ++i) ++hist[key_of(i) + 1];
     for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
+    std::vector<int> band_start((size_t)nbands + 1, 0);
+    for (int k = 0; k <= nbands; ++k) band_start[(size_t)k] = hist[std::min(nkeys, (size_t)k * (size_t)(max_border + 1))];
     int typ_border = max_border;
     {   // median border = typical point
-        long long half = n / 2;
-        for (int b = 0; b <= max_border; ++b) if (hist[(size_t)b + 1] > half) { typ_border = max_border - b; break; }
+        std::vector<long long> per_b((size_t)max_border + 1, 0);
+        for (int64_t i = 0; i < n; ++i) ++per_b[(size_t)ib[(size_t)i]];
+        long long acc = 0;
+        for (int b = max_border; b >= 0; --b) { acc += per_b[(size_t)b]; if (acc > n / 2) { typ_border = b; break; } }
     }
 
     const size_t pts_bytes = (size_t)n * 5 * sizeof(double);
@@ -384,17 +433,61 @@ int sid_run(sid_ctx *ctx, int64_t n, const double *c1, const double *r1, const d
     memcpy(hp, c1, (size_t)n * 8); memcpy(hp + n, r1, (size_t)n * 8); memcpy(hp + 2 * n, c2fg, (size_t)n * 8);
     memcpy(hp + 3 * n, r2fg, (size_t)n * 8); memcpy(hp + 4 * n, border, (size_t)n * 8);
     int *hord = (int *)((char *)ctx->pin + pts_bytes);
-    for (int64_t i = 0; i < n; ++i) hord[hist[(size_t)(max_border - ib[(size_t)i])]++] = (int)i;
+    for (int64_t i = 0; i < n; ++i) hord[hist[key_of(i)]++] = (int)i;
+
+    // ---- small uploads FIRST: host-to-device copies of all streams share the copy engine in issue order,
+    //      so anything enqueued behind the image bands would hold the first kernel back until they are done
     CU(cudaMemcpyAsync(ctx->pts.p, hp, pts_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->order.p, hord, ord_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const double *d_angles, *d_tab;
     if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab))) return rc;
 
+    // ---- image upload in bands on the copy stream
+    if (pair) {
+        ctx->have_pair = false;
+        if (!ctx->copy_stream) {
+            CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int k = 0; k <= MAX_BANDS; ++k) CU(cudaEventCreateWithFlags(&ctx->band_event[k], cudaEventDisableTiming));
+        }
+        ctx->pitch1 = padded_pitch(pair->cols1);
+        ctx->pitch2 = padded_pitch(pair->cols2);
+        const size_t b1 = (size_t)ctx->pitch1 * pair->rows1 + IMG_TAIL_SLACK, b2 = (size_t)ctx->pitch2 * pair->rows2 + IMG_TAIL_SLACK;
+        const bool fresh1 = b1 > ctx->img1.cap, fresh2 = b2 > ctx->img2.cap;
+        if ((rc = reserve(ctx, ctx->img1, b1))) return rc;
+        if ((rc = reserve(ctx, ctx->img2, b2))) return rc;
+        // the copy stream must not overwrite images an earlier launch on the compute stream still reads
+        CU(cudaEventRecord(ctx->band_event[MAX_BANDS], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->band_event[MAX_BANDS], 0));
+        if (fresh1) CU(cudaMemsetAsync(ctx->img1.p, 0, ctx->img1.cap, ctx->copy_stream));
+        if (fresh2) CU(cudaMemsetAsync(ctx->img2.p, 0, ctx->img2.cap, ctx->copy_stream));
+        for (int k = 0; k < nbands; ++k) {
+            const int ya = k * band_rows;
+            const int n1 = std::min(band_rows, pair->rows1 - ya), n2 = std::min(band_rows, pair->rows2 - ya);
+            if (n1 > 0)
+                CU(cudaMemcpy2DAsync((char *)ctx->img1.p + (size_t)ya * ctx->pitch1, (size_t)ctx->pitch1,
+                                     pair->img1 + (size_t)ya * pair->pitch1, (size_t)pair->pitch1, (size_t)pair->cols1,
+                                     (size_t)n1, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (n2 > 0)
+                CU(cudaMemcpy2DAsync((char *)ctx->img2.p + (size_t)ya * ctx->pitch2, (size_t)ctx->pitch2,
+                                     pair->img2 + (size_t)ya * pair->pitch2, (size_t)pair->pitch2, (size_t)pair->cols2,
+                                     (size_t)n2, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaEventRecord(ctx->band_event[k], ctx->copy_stream));
+        }
+        ctx->rows1 = pair->rows1; ctx->cols1 = pair->cols1; ctx->rows2 = pair->rows2; ctx->cols2 = pair->cols2;
+    }
+
+
     const double *dp = (const double *)ctx->pts.p;
-    rc = launch_pm(ctx, n, dp, dp + n, dp + 2 * n, dp + 3 * n, dp + 4 * n, (const int *)ctx->order.p,
-                   max_border, typ_border, img_size, n_angles, d_angles, d_tab, rot_order, flags,
-                   (double *)ctx->out.p, (int *)ctx->status.p);
-    if (rc) return rc;
+    for (int k = 0; k < nbands; ++k) {
+        if (pair) CU(cudaStreamWaitEvent(ctx->stream, ctx->band_event[k], 0));
+        const int lo = band_start[(size_t)k], hi = band_start[(size_t)k + 1];
+        if (hi <= lo) continue;
+        rc = launch_pm(ctx, hi - lo, dp, dp + n, dp + 2 * n, dp + 3 * n, dp + 4 * n, (const int *)ctx->order.p + lo,
+                       max_border, typ_border, img_size, n_angles, d_angles, d_tab, rot_order, flags,
+                       (double *)ctx->out.p, (int *)ctx->status.p);
+        if (rc) return rc;
+    }
+    if (pair) ctx->have_pair = true;
     double *hout = (double *)((char *)ctx->pin + pts_bytes + ord_bytes);
     int *hst = (int *)((char *)hout + out_bytes);
     CU(cudaMemcpyAsync(hout, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -404,6 +497,26 @@ int sid_run(sid_ctx *ctx, int64_t n, const double *c1, const double *r1, const d
     memcpy(out, hout, out_bytes);
     if (status) memcpy(status, hst, st_bytes);
     return SID_OK;
+}
+
+}  // namespace
+
+int sid_run(sid_ctx *ctx, int64_t n, const double *c1, const double *r1, const double *c2fg,
+            const double *r2fg, const double *border, int img_size, int n_angles, const double *angles,
+            const double *angle_tab, int rot_order, unsigned flags, int mtype, double *out, int *status) {
+    return run_host(ctx, nullptr, n, c1, r1, c2fg, r2fg, border, img_size, n_angles, angles, angle_tab, rot_order,
+                    flags, mtype, out, status);
+}
+
+int sid_run_pair(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
+                 const uint8_t *img2, int rows2, int cols2, int64_t pitch2,
+                 int64_t n, const double *c1, const double *r1, const double *c2fg,
+                 const double *r2fg, const double *border, int img_size, int n_angles, const double *angles,
+                 const double *angle_tab, int rot_order, unsigned flags, int mtype, double *out, int *status) {
+    if (!ctx) return SID_EINVAL;
+    HostPair hp{img1, img2, rows1, cols1, rows2, cols2, (long long)pitch1, (long long)pitch2};
+    return run_host(ctx, &hp, n, c1, r1, c2fg, r2fg, border, img_size, n_angles, angles, angle_tab, rot_order,
+                    flags, mtype, out, status);
 }
 
 int sid_run_device(sid_ctx *ctx, int64_t n, const double *d_c1, const double *d_r1, const double *d_c2fg,

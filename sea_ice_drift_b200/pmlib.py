@@ -126,11 +126,18 @@ def use_mcc_batch(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, **kw
         rows = [use_mcc(a, b, c, d, e, img1, img2, img_size, alpha0, **kwargs)
                 for a, b, c, d, e in zip(c1, r1, c2fg, r2fg, border)]
         return np.array(rows, dtype=np.float64).reshape(-1, 5)
-    ctx = _ensure_pair(_ctx(kwargs), img1, img2)
+    ctx = _ctx(kwargs)
     flags = flags_from_kwargs(kwargs.get('hes_norm', True), kwargs.get('hes_smth', False),
                               kwargs.get('mcc_norm', False))
-    return ctx.run(c1, r1, c2fg, r2fg, border, img_size, list(kwargs.get('angles', [-3, 0, 3])), alpha0,
-                   kwargs.get('rot_order', 0), flags, kwargs.get('mtype', TM_CCOEFF_NORMED))
+    args = (c1, r1, c2fg, r2fg, border, img_size, list(kwargs.get('angles', [-3, 0, 3])), alpha0,
+            kwargs.get('rot_order', 0), flags, kwargs.get('mtype', TM_CCOEFF_NORMED))
+    key = (_pair_fingerprint(img1), _pair_fingerprint(img2))
+    if _pair_cache.get(id(ctx)) == key and ctx._pair_key == key:
+        return ctx.run(*args)                      # pair already resident
+    out = ctx.run_pair(img1, img2, *args)          # upload overlapped with the matching
+    ctx._pair_key = key
+    _pair_cache[id(ctx)] = key
+    return out
 
 
 def use_mcc(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, **kwargs):

@@ -216,3 +216,40 @@ def test_pattern_matching_drop_in_end_to_end(monkeypatch):
     with contextlib.redirect_stdout(io.StringIO()):
         u = drift.get_drift_PM(lon, lat, lon1, lat1, lon2, lat2, angles=[-3, 0, 3])[0]
     assert np.array_equal(u, gpu[0], equal_nan=True)
+
+
+def test_run_pair_overlapped_upload_equals_set_pair_then_run(gpu_ctx):
+    """sid_run_pair (banded upload overlapped with compute) == sid_set_pair + sid_run, bit for bit."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=7, side=5200, grid=70)
+    b = np.floor(np.random.default_rng(3).uniform(20, 41, b.size))
+    gpu_ctx.set_pair(img1, img2)
+    ref, st_ref = gpu_ctx.run(c1, r1, c2, r2, b, 35, cfg["angles"], 0.0, want_status=True)
+    other = np.ascontiguousarray(img1[::-1])                       # make the resident pair stale first
+    gpu_ctx.set_pair(other, other)
+    got, st = gpu_ctx.run_pair(img1, img2, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0, want_status=True)
+    assert np.array_equal(got, ref, equal_nan=True) and np.array_equal(st, st_ref)
+    again = gpu_ctx.run(c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)       # the pair stays resident
+    assert np.array_equal(again, ref, equal_nan=True)
+    # pitched views of larger arrays are uploaded as they are
+    big1 = np.zeros((5300, 5400), np.uint8); big1[50:5250, 100:5300] = img1
+    big2 = np.zeros((5300, 5400), np.uint8); big2[50:5250, 100:5300] = img2
+    got2 = gpu_ctx.run_pair(big1[50:5250, 100:5300], big2[50:5250, 100:5300], c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
+    assert np.array_equal(got2, ref, equal_nan=True)
+    empty = gpu_ctx.run_pair(img1, img2, [], [], [], [], [], 35, cfg["angles"], 0.0)
+    assert empty.shape == (0, 5)
+
+
+def test_sharded_pattern_matching_over_nccl_two_gpus():
+    """Strong scaling path on real GPUs: 2 ranks, NCCL all-gather (skipped on a 1-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tests", "multi_gpu_sharded.py")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert "== single GPU: True" in res.stdout
