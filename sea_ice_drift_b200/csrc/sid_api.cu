@@ -1,5 +1,6 @@
 // sid_api.cu -- C ABI (include/sid_b200.h) over the sm_100a kernels.
 // No exceptions cross the boundary; every entry point returns a SID_* code.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -48,6 +49,8 @@ struct sid_ctx {
     void *pin = nullptr;
     size_t pin_cap = 0;
     int attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void *encode_tiled = nullptr;            // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
+    bool encode_tried = false;
 };
 
 namespace {
@@ -119,6 +122,33 @@ int check_common(sid_ctx *ctx, int img_size, int n_angles, const double *angle_t
     return SID_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// uint8 2-D tensor map over image 2 with a box of box_w x box_h bytes (TMA window staging).
+bool make_window_tensor_map(sid_ctx *ctx, CUtensorMap *map, int box_w, int box_h) {
+    if (!ctx->encode_tried) {
+        ctx->encode_tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            ctx->encode_tiled = fn;
+        else
+            cudaGetLastError();
+    }
+    if (!ctx->encode_tiled || box_w > 256 || box_h > 256 || (box_w & 15) || (ctx->pitch2 & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ctx->cols2, (cuuint64_t)ctx->rows2};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ctx->pitch2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->img2.p, gdim, gstride, box,
+                                                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // shared launch path of sid_run / sid_run_device
 int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1, const double *d_c2fg,
               const double *d_r2fg, const double *d_border, const int *d_order, int max_border, int typ_border,
@@ -147,7 +177,20 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     // correlation path: tensor cores (IMMA, exact u8 x u8 -> s32) unless SID_PM_PATH=dp4a
     const char *path_env = getenv("SID_PM_PATH");
     const bool imma = !(path_env && strcmp(path_env, "dp4a") == 0);
-    const int wpw = pm_window_pitch_words(Wmax, imma);
+    // window staging by TMA when the padded window (+15 bytes: the box must start 16-byte aligned) fits one
+    // box of <= 256 x 256 bytes
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    a.tma = 0;
+    int wpw = pm_window_pitch_words(Wmax, imma);
+    {
+        const char *e = getenv("SID_PM_TMA");
+        const int wpw_tma = pm_window_pitch_words(Wmax + 15, imma);
+        if (!(e && e[0] == '0') && make_window_tensor_map(ctx, &tmap, wpw_tma * 4, Wmax)) {
+            a.tma = 1; a.tma_wpw = wpw_tma; a.tma_rows = Wmax;
+            wpw = wpw_tma;
+        }
+    }
     a.win_words = (Wmax + (imma ? PM_IMMA_ROW_SLACK : 0)) * wpw + PM_WIN_SLACK;
     const int nw = (s + 3) / 4;
     int variant;                      // dp4a kernel specialisation by template width in words
@@ -239,7 +282,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     a.counter = (unsigned int *)ctx->counter.p;
     CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
 
-    void *params[] = {(void *)&a};
+    void *params[] = {(void *)&a, (void *)&tmap};
     CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, ctx->stream));
     ctx->launches += 1;
     return SID_OK;

@@ -32,6 +32,7 @@ struct BlockScratch {
     double red[32];
     uint32_t hist[256];
     uint32_t sel[2];
+    uint32_t wtot[32];
 };
 
 __device__ __forceinline__ double block_sum(double v, BlockScratch &bs) {
@@ -96,8 +97,75 @@ __device__ float block_select(const float *__restrict__ d, int n, int k, BlockSc
     return key_f32(prefix);
 }
 
+// Same selection with 11/11/10-bit digits (3 passes) on a caller-provided 2048-bin histogram
+// (shared memory that is free at that point of the kernel).
+__device__ float block_select_wide(const float *__restrict__ d, int n, int k, uint32_t *__restrict__ hist, BlockScratch &bs) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t prefix = 0, mask = 0;
+    uint32_t kk = (uint32_t)k;
+    const int iters = (n + nt - 1) / nt;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const int bits = pass == 2 ? 10 : 11;
+        const int nbins = 1 << bits;
+        for (int i = tid; i < nbins; i += nt) hist[i] = 0;
+        __syncthreads();
+        for (int it = 0; it < iters; ++it) {
+            const int i = it * nt + tid;
+            uint32_t bin = 0xffffffffu;
+            if (i < n) {
+                const uint32_t key = f32_key(d[i]);
+                if ((key & mask) == prefix) bin = (key >> shift) & (uint32_t)(nbins - 1);
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+        }
+        __syncthreads();
+        {   // rank search over the histogram with the whole CTA: per-thread chunk sums, block-wide exclusive
+            // scan, then the single owning thread walks its chunk
+            const int per = (nbins + nt - 1) / nt;
+            const int b0 = tid * per;
+            uint32_t s = 0;
+            for (int j = 0; j < per; ++j) if (b0 + j < nbins) s += hist[b0 + j];
+            uint32_t incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) bs.wtot[warp] = incl;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int w = 0; w < warp; ++w) woff += bs.wtot[w];
+            const uint32_t excl = woff + incl - s;
+            if (kk >= excl && kk < excl + s) {
+                uint32_t c = excl;
+                for (int j = 0; j < per; ++j) {
+                    const uint32_t h = hist[b0 + j];
+                    if (kk < c + h) { bs.sel[0] = b0 + j; bs.sel[1] = kk - c; break; }
+                    c += h;
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= bs.sel[0] << shift;
+        mask |= (uint32_t)(nbins - 1) << shift;
+        kk = bs.sel[1];
+        __syncthreads();
+    }
+    return key_f32(prefix);
+}
+
 // np.median of n float32 values (no NaN handling needed: NCC maps are finite).
-__device__ float block_median(const float *__restrict__ d, int n, BlockScratch &bs) {
+// `wide_hist`: optional 2048-word shared-memory scratch enabling the 3-pass variant.
+__device__ float block_median(const float *__restrict__ d, int n, BlockScratch &bs, uint32_t *wide_hist = nullptr) {
+    if (wide_hist) {
+        if (n & 1) return block_select_wide(d, n, n / 2, wide_hist, bs);
+        const float a = block_select_wide(d, n, n / 2 - 1, wide_hist, bs);
+        const float b = block_select_wide(d, n, n / 2, wide_hist, bs);
+        return __fmul_rn(__fadd_rn(a, b), 0.5f);
+    }
     if (n & 1) return block_select(d, n, n / 2, bs);
     const float a = block_select(d, n, n / 2 - 1, bs);
     const float b = block_select(d, n, n / 2, bs);
@@ -293,7 +361,7 @@ struct PeakStats { float h; float r; };
 __device__ PeakStats peak_statistics(const float *__restrict__ best, int rows, int cols, int peak_idx, float peak_r,
                                      unsigned flags, const double *gw,
                                      float *__restrict__ tmp_a, float *__restrict__ tmp_b, float *__restrict__ hes,
-                                     BlockScratch &bs) {
+                                     BlockScratch &bs, uint32_t *wide_hist = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x, n = rows * cols;
     const int y_first = tid / cols, x_first = tid - y_first * cols, dy = nt / cols, dx = nt - dy * cols;
     const float *src = best;
@@ -344,16 +412,41 @@ __device__ PeakStats peak_statistics(const float *__restrict__ best, int rows, i
     ps.h = hes[peak_idx];
     ps.r = peak_r;
     if (flags & 1u) {               // hes_norm
-        const float med = block_median(hes, n, bs);
+        const float med = block_median(hes, n, bs, wide_hist);
         const float sd = block_std(hes, n, bs);
         ps.h = __fdiv_rn(__fsub_rn(ps.h, med), sd);
     }
     if (flags & 4u) {               // mcc_norm
-        const float med = block_median(best, n, bs);
+        const float med = block_median(best, n, bs, wide_hist);
         const float sd = block_std(best, n, bs);
         ps.r = __fdiv_rn(__fsub_rn(peak_r, med), sd);
     }
     return ps;
+}
+
+// ---------------------------------------------------------------- TMA (cp.async.bulk.tensor) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 2-D tile of a uint8 image -> shared memory; (x, y) = element coordinates of the tile's first byte
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, unsigned long long *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy accesses to dst are done
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---------------------------------------------------------------- argmax helpers

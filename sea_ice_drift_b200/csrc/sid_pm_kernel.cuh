@@ -24,6 +24,7 @@
 // slab that stays L2-resident; only O(R^2) traffic per angle goes there, against
 // O(R^2 s^2) integer MACs out of shared memory / registers.
 #pragma once
+#include <cuda.h>
 #include "sid_common.cuh"
 
 namespace sid {
@@ -59,6 +60,8 @@ struct PmArgs {
     int ab;                       // angles per batch
     int tpl_off;                  // byte offset of template column 0 inside a template row (IMMA path: 8)
     int nc;                       // IMMA path: 32-byte K chunks per template row = ceil((s + 7) / 32)
+    int tma;                      // 1: stage the window with a TMA 2-D tile load (box = tma_wpw*4 x tma_rows bytes)
+    int tma_wpw, tma_rows;
     unsigned int *counter;        // work-stealing cursor
 };
 
@@ -143,11 +146,13 @@ struct PmShared {
 template <int TX, int NW>
 __device__ __forceinline__ void pm_tiles(const uint32_t *__restrict__ win32, int wpw,
                                          const uint32_t *__restrict__ tpl32, int tpw, int s,
-                                         int nb, int RH, int RW,
+                                         int nb, int RH, int RW, int ab,
                                          const uint32_t *__restrict__ wsum, const double *__restrict__ wden,
                                          float *__restrict__ maps, int max_rr, PmShared &S) {
+    // `ab` (0..3): byte offset of window column 0 inside win32's first word (TMA staging starts 16-byte
+    // aligned); tiles are laid out over shifted columns x' = x + ab and mapped back on output
     const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
-    const int nwc = (RW + 3) >> 2;
+    const int nwc = (RW + ab + 3) >> 2;
     const int ncg = (nwc + TX - 1) / TX;
     const int ntiles = nb * ncg * RH * 4;
     const int nchunk = (s + 15) / 16;
@@ -174,8 +179,8 @@ __device__ __forceinline__ void pm_tiles(const uint32_t *__restrict__ win32, int
             my_ai = ai;
 #pragma unroll
             for (int tx = 0; tx < TX; ++tx) {
-                const int x = 4 * (q0 + tx) + p;
-                if (x < RW) {
+                const int x = 4 * (q0 + tx) + p - ab;
+                if (x >= 0 && x < RW) {
                     const int idx = y * RW + x;
                     const float v = ncc_value((long long)acc[tx], wsum[idx], wden[idx], st);
                     map[idx] = v;
@@ -195,15 +200,15 @@ __device__ __forceinline__ void pm_tiles(const uint32_t *__restrict__ win32, int
 
 template <int NW>
 __device__ __forceinline__ void pm_tiles_dispatch(int tx, const uint32_t *win32, int wpw, const uint32_t *tpl32, int tpw,
-                                                  int s, int nb, int RH, int RW, const uint32_t *wsum,
+                                                  int s, int nb, int RH, int RW, int ab, const uint32_t *wsum,
                                                   const double *wden, float *maps, int max_rr, PmShared &S) {
     switch (tx) {
-        case 8: pm_tiles<8, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
-        case 9: pm_tiles<9, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
-        case 10: pm_tiles<10, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
-        case 11: pm_tiles<11, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
-        case 12: pm_tiles<12, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
-        default: pm_tiles<13, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, max_rr, S); break;
+        case 8: pm_tiles<8, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, ab, wsum, wden, maps, max_rr, S); break;
+        case 9: pm_tiles<9, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, ab, wsum, wden, maps, max_rr, S); break;
+        case 10: pm_tiles<10, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, ab, wsum, wden, maps, max_rr, S); break;
+        case 11: pm_tiles<11, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, ab, wsum, wden, maps, max_rr, S); break;
+        case 12: pm_tiles<12, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, ab, wsum, wden, maps, max_rr, S); break;
+        default: pm_tiles<13, NW>(win32, wpw, tpl32, tpw, s, nb, RH, RW, ab, wsum, wden, maps, max_rr, S); break;
     }
 }
 
@@ -225,12 +230,12 @@ __device__ __forceinline__ void mma_u8_16832(int (&c)[4], uint32_t a0, uint32_t 
 template <int NBA, int NC>   // NC > 0: compile-time number of 32-byte K chunks (2 covers img_size <= 57)
 __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32, int wpw,
                                               const uint32_t *__restrict__ tpl32, int tpw, int s, int nc_rt,
-                                              int RH, int RW,
+                                              int RH, int RW, int ab,
                                               const uint32_t *__restrict__ wsum, const double *__restrict__ wden,
                                               float *__restrict__ maps, int max_rr, PmShared &S) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, tig = lane & 3;
-    const int nxg = (RW + 23) / 24;
+    const int nxg = (RW + ab + 23) / 24;               // tiles over shifted columns x' = x + ab (see pm_tiles)
     const int ntiles = ((RH + 15) >> 4) * nxg;
     const int ob = 8 + 8 * tig - g;               // byte offset of this lane's B bytes inside a padded template row
     const int bw = ob >> 2, bsh = (ob & 3) * 8;
@@ -285,8 +290,8 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int y = y0 + g + 8 * h, x = x0 + 8 * b + 2 * tig + e;
-                    if (y < RH && x < RW) {
+                    const int y = y0 + g + 8 * h, x = x0 + 8 * b + 2 * tig + e - ab;
+                    if (y < RH && x >= 0 && x < RW) {
                         const int idx = y * RW + x;
                         const uint32_t ws = wsum[idx];
                         const double wd = wden[idx];
@@ -332,9 +337,12 @@ __host__ __device__ inline size_t pm_scratch_bytes(int max_rr, int max_hrw, int 
 // windows: no L2 round trips in the statistics / epilogue / Hessian / median phases); otherwise
 // in this CTA's global slab (any window size).
 template <int NW, bool SMEM_SCRATCH, bool IMMA>
-__global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_points_kernel(const PmArgs a) {
-    extern __shared__ __align__(16) unsigned char pm_smem[];
+__global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3)
+pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
+    extern __shared__ __align__(128) unsigned char pm_smem[];
     __shared__ PmShared S;
+    __shared__ __align__(8) unsigned long long win_bar;
+    unsigned win_phase = 0;
     uint32_t *win32 = reinterpret_cast<uint32_t *>(pm_smem);
     uint32_t *tpl32 = win32 + a.win_words;
     const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;   // nt <= PM_THREADS, chosen by the host
@@ -349,7 +357,10 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
     uint32_t *hs = reinterpret_cast<uint32_t *>(maps);          // aliases the maps: dead before the first map is written
     uint32_t *hq = hs + a.max_hrw;
 
-    if (tid == 0) S.next = atomicAdd(a.counter, 1u);
+    if (tid == 0) {
+        S.next = atomicAdd(a.counter, 1u);
+        if (a.tma) mbar_init(&win_bar, 1);
+    }
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -379,7 +390,10 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
         }
         const int H = (int)(y1 - y0), W = (int)(x1 - x0);
         const int RH = H - s + 1, RW = W - s + 1, RR = RH * RW;
-        const int wpw = pm_window_pitch_words(W, IMMA);
+        const int wpw = a.tma ? a.tma_wpw : pm_window_pitch_words(W, IMMA);
+        const int xoff = a.tma ? (int)(x0 & 15) : 0;          // byte offset of window column 0 inside a staged row
+        const int xab = xoff & 3;
+        const uint32_t *winx = win32 + (xoff >> 2);
         if (ok) ok = RR <= a.max_rr && H * RW <= a.max_hrw &&
                      (H + (IMMA ? PM_IMMA_ROW_SLACK : 0)) * wpw + PM_WIN_SLACK <= a.win_words;
         if (!ok) {
@@ -390,25 +404,37 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
             continue;
         }
 
-        // ---- 1. stage the window, word-aligned: one warp per row, each lane loads one aligned word and
-        //         takes its right neighbour by shuffle; two rows in flight per warp
-        {
+        // ---- 1. stage the window.  TMA: one 2-D tile load of the uint8 image (any byte offset, out-of-image
+        //         bytes read as 0) signalled on an mbarrier.  Otherwise: one warp per row, each lane loads one
+        //         aligned word and takes its right neighbour by shuffle, four rows in flight per warp.
+        if (a.tma) {
+            if (tid == 0) {
+                mbar_expect_tx(&win_bar, (unsigned)(a.tma_wpw * 4 * a.tma_rows));
+                tma_load_2d(win32, &tmap2, (int)x0 - xoff, (int)y0, &win_bar);   // innermost start must be 16-byte aligned
+                S.best_r = -INFINITY; S.best_a = -1; S.best_idx = 0; S.best_slot = -1;
+            }
+            mbar_wait(&win_bar, win_phase);
+            win_phase ^= 1u;
+        } else {
             const int al8 = 8 * (int)(x0 & 3);
             const unsigned char *g = a.img2 + y0 * a.pitch2 + (x0 - (x0 & 3));
             const int warp = tid >> 5, nwarps = nt >> 5;
             for (int kb = 0; kb < wpw; kb += 31) {                  // 31 output words per pass (lane 31 only feeds lane 30)
                 const int k = kb + lane;
                 const bool in_row = k <= wpw;                        // word wpw is read for the last shift only
-                for (int y = warp; y < H; y += 2 * nwarps) {
-                    const int yb = y + nwarps;
-                    const uint32_t *ga = reinterpret_cast<const uint32_t *>(g + (long long)y * a.pitch2);
-                    const uint32_t *gb = reinterpret_cast<const uint32_t *>(g + (long long)yb * a.pitch2);
-                    uint32_t wa = 0, wb = 0;
-                    if (in_row) { wa = __ldg(ga + k); if (yb < H) wb = __ldg(gb + k); }
-                    const uint32_t na = __shfl_down_sync(0xffffffffu, wa, 1), nb2 = __shfl_down_sync(0xffffffffu, wb, 1);
-                    if (lane < 31 && k < wpw) {
-                        win32[y * wpw + k] = __funnelshift_r(wa, na, al8);
-                        if (yb < H) win32[yb * wpw + k] = __funnelshift_r(wb, nb2, al8);
+                for (int y = warp; y < H; y += 4 * nwarps) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int yy = y + u * nwarps;
+                        w[u] = 0;
+                        if (in_row && yy < H) w[u] = __ldg(reinterpret_cast<const uint32_t *>(g + (long long)yy * a.pitch2) + k);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int yy = y + u * nwarps;
+                        const uint32_t nx = __shfl_down_sync(0xffffffffu, w[u], 1);
+                        if (lane < 31 && k < wpw && yy < H) win32[yy * wpw + k] = __funnelshift_r(w[u], nx, al8);
                     }
                 }
             }
@@ -420,11 +446,13 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
         {
             const unsigned char *wb = reinterpret_cast<const unsigned char *>(win32);
             const int pitchb = wpw * 4;
-            const int nseg = (RW + PM_SEG - 1) / PM_SEG;
+            int seg = PM_SEG;                                         // one round: H * ceil(RW / seg) <= nt when possible
+            while (H * ((RW + seg - 1) / seg) > nt && seg < RW) ++seg;
+            const int nseg = (RW + seg - 1) / seg;
             for (int t = tid; t < H * nseg; t += nt) {
-                const int y = t / nseg, xs = (t - y * nseg) * PM_SEG;
-                const int xe = min(RW, xs + PM_SEG);
-                const unsigned char *rowp = wb + y * pitchb;
+                const int y = t / nseg, xs = (t - y * nseg) * seg;
+                const int xe = min(RW, xs + seg);
+                const unsigned char *rowp = wb + y * pitchb + xoff;
                 uint32_t sum = 0, sq = 0;
                 for (int j = 0; j < s; ++j) { const uint32_t v = rowp[xs + j]; sum += v; sq += v * v; }
                 for (int x = xs; x < xe; ++x) {
@@ -437,10 +465,12 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
         __syncthreads();
         // ---- 2b. vertical sliding sums -> window sum and denominator per displacement
         {
-            const int nseg = (RH + PM_VSEG - 1) / PM_VSEG;
+            int vseg = PM_VSEG;                                       // one round: RW * ceil(RH / vseg) <= nt when possible
+            while (RW * ((RH + vseg - 1) / vseg) > nt && vseg < RH) ++vseg;
+            const int nseg = (RH + vseg - 1) / vseg;
             for (int t = tid; t < RW * nseg; t += nt) {
                 const int sg = t / RW, x = t - sg * RW;
-                const int ys = sg * PM_VSEG, ye = min(RH, ys + PM_VSEG);
+                const int ys = sg * vseg, ye = min(RH, ys + vseg);
                 uint32_t sum = 0, sq = 0;
 #pragma unroll 5
                 for (int i = 0; i < s; ++i) { sum += hs[(ys + i) * RW + x]; sq += hq[(ys + i) * RW + x]; }
@@ -460,7 +490,7 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
         const int A = a.n_angles;
         const int nbatch = (A + ab - 1) / ab;
         const int per = (A + nbatch - 1) / nbatch;
-        const int txsel = pm_pick_tx(RW);
+        const int txsel = pm_pick_tx(RW + xab);
         bool has_zero = false;
         for (int a0 = 0; a0 < A; a0 += per) {
             const int nb = min(per, A - a0);
@@ -481,25 +511,27 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
                     const double cs = tab[0], sn = tab[1];
                     const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
                     const bool inside = template_inside_warp(a.rows1, a.cols1, off0, off1, cs, sn, s);
+                    const bool fast0 = inside && a.rot_order == 0;      // common case: nearest neighbour, fully inside
                     const double jsn = __dmul_rn(dj, sn), jcs = __dmul_rn(dj, cs);
                     unsigned char *tdst = tb + (size_t)ai * s * tpw * 4 + a.tpl_off + gj;
                     uint32_t lsum = 0, lsq = 0; int lzero = 0;
-                    for (int i0 = 0; i0 < s; i0 += 4 * rows_per_pass) {
-                        uint32_t v[4];
+                    for (int i0 = 0; i0 < s; i0 += 8 * rows_per_pass) {
+                        uint32_t v[8];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 8; ++u) {
                             const int i = i0 + u * rows_per_pass + gi;
                             v[u] = 1u;
                             if (active && i < s) {
                                 const double di = (double)i;
                                 const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), jsn);
                                 const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), jcs);
-                                v[u] = inside ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order)
-                                              : template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order);
+                                v[u] = fast0 ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0)
+                                             : (inside ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order)
+                                                       : template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order));
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 8; ++u) {
                             const int i = i0 + u * rows_per_pass + gi;
                             if (active && i < s) {
                                 tdst[i * tpw * 4] = (unsigned char)v[u];
@@ -528,16 +560,16 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
             __syncthreads();
             if constexpr (IMMA) {
                 if (a.nc == 2) {
-                    if (nb == 1) pm_tiles_imma<1, 2>(win32, wpw, tpl32, tpw, s, 2, RH, RW, wsum, wden, maps, a.max_rr, S);
-                    else if (nb == 2) pm_tiles_imma<2, 2>(win32, wpw, tpl32, tpw, s, 2, RH, RW, wsum, wden, maps, a.max_rr, S);
-                    else pm_tiles_imma<3, 2>(win32, wpw, tpl32, tpw, s, 2, RH, RW, wsum, wden, maps, a.max_rr, S);
+                    if (nb == 1) pm_tiles_imma<1, 2>(winx, wpw, tpl32, tpw, s, 2, RH, RW, xab, wsum, wden, maps, a.max_rr, S);
+                    else if (nb == 2) pm_tiles_imma<2, 2>(winx, wpw, tpl32, tpw, s, 2, RH, RW, xab, wsum, wden, maps, a.max_rr, S);
+                    else pm_tiles_imma<3, 2>(winx, wpw, tpl32, tpw, s, 2, RH, RW, xab, wsum, wden, maps, a.max_rr, S);
                 } else {
-                    if (nb == 1) pm_tiles_imma<1, 0>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
-                    else if (nb == 2) pm_tiles_imma<2, 0>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
-                    else pm_tiles_imma<3, 0>(win32, wpw, tpl32, tpw, s, a.nc, RH, RW, wsum, wden, maps, a.max_rr, S);
+                    if (nb == 1) pm_tiles_imma<1, 0>(winx, wpw, tpl32, tpw, s, a.nc, RH, RW, xab, wsum, wden, maps, a.max_rr, S);
+                    else if (nb == 2) pm_tiles_imma<2, 0>(winx, wpw, tpl32, tpw, s, a.nc, RH, RW, xab, wsum, wden, maps, a.max_rr, S);
+                    else pm_tiles_imma<3, 0>(winx, wpw, tpl32, tpw, s, a.nc, RH, RW, xab, wsum, wden, maps, a.max_rr, S);
                 }
             } else {
-                pm_tiles_dispatch<NW>(txsel, win32, wpw, tpl32, tpw, s, nb, RH, RW, wsum, wden, maps, a.max_rr, S);
+                pm_tiles_dispatch<NW>(txsel, winx, wpw, tpl32, tpw, s, nb, RH, RW, xab, wsum, wden, maps, a.max_rr, S);
             }
             __syncthreads();
             if (tid == 0) {
@@ -567,7 +599,9 @@ __global__ void __launch_bounds__(IMMA ? PM_IMMA_THREADS : PM_THREADS, 3) pm_poi
         float *tmp_a = maps + (size_t)(best_slot == 0 ? 1 : 0) * a.max_rr;
         float *hes = maps + (size_t)(ab + 1) * a.max_rr;
         float *tmp_b = maps + (size_t)(ab + 2) * a.max_rr;      // only allocated (and touched) with hes_smth
-        const PeakStats ps = peak_statistics(best, RH, RW, best_idx, S.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, S.bs);
+        uint32_t *wide_hist = nullptr;                      // 2048 bins on the window-statistics buffer (dead by now)
+        if constexpr (SMEM_SCRATCH) { if ((size_t)a.max_rr * 8 >= 2048 * 4) wide_hist = reinterpret_cast<uint32_t *>(wden); }
+        const PeakStats ps = peak_statistics(best, RH, RW, best_idx, S.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, S.bs, wide_hist);
         if (tid == 0) {
             const int bi = best_idx / RW, bj = best_idx - bi * RW;
             const double dr = (double)bi - (double)(H - s) / 2.0;
