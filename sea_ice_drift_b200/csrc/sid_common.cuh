@@ -221,6 +221,17 @@ __device__ __forceinline__ double window_den(uint32_t wsum, uint32_t wsq, double
     return diff2 <= thr ? 0.0 : __dsqrt_rn(diff2);
 }
 
+// out-of-line copy for call sites that would otherwise inline dozens of instances (instruction-cache footprint)
+__device__ __noinline__ float ncc_value_call(int corr, uint32_t wsum, double wden, double mean, double norm) {
+    double num = __dsub_rn((double)corr, __dmul_rn((double)wsum, mean));
+    const double t = __dmul_rn(wden, norm);
+    const double an = fabs(num);
+    if (an < t) num = __ddiv_rn(num, t);
+    else if (an < __dmul_rn(t, 1.125)) num = num > 0.0 ? 1.0 : -1.0;
+    else num = 0.0;
+    return __double2float_rn(num);
+}
+
 __device__ __forceinline__ float ncc_value(int64_t corr, uint32_t wsum, double wden, const TemplStats &st) {
     if (st.flat) return 1.0f;
     double num = __dsub_rn((double)corr, __dmul_rn((double)wsum, st.mean));

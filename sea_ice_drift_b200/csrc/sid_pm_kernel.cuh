@@ -297,7 +297,8 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
                         const double wd = wden[idx];
 #pragma unroll
                         for (int a = 0; a < NBA; ++a) {
-                            const float v = ncc_value((long long)acc[a][b][2 * h + e], ws, wd, S.st[a]);
+                            const float v = S.st[a].flat ? 1.0f
+                                                         : ncc_value_call(acc[a][b][2 * h + e], ws, wd, S.st[a].mean, S.st[a].norm);
                             maps[(size_t)S.slot[a] * max_rr + idx] = v;
                             const unsigned long long k2 = peak_key(v, (uint32_t)idx);
                             key[a] = k2 > key[a] ? k2 : key[a];
@@ -515,30 +516,34 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
                     const double jsn = __dmul_rn(dj, sn), jcs = __dmul_rn(dj, cs);
                     unsigned char *tdst = tb + (size_t)ai * s * tpw * 4 + a.tpl_off + gj;
                     uint32_t lsum = 0, lsq = 0; int lzero = 0;
-                    for (int i0 = 0; i0 < s; i0 += 8 * rows_per_pass) {
-                        uint32_t v[8];
+                    // one specialised loop runs per template: nearest + inside (the common case), other inside, checked
+                    auto sweep = [&](auto sample) {
+                        for (int i0 = 0; i0 < s; i0 += 4 * rows_per_pass) {
+                            uint32_t v[4];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int i = i0 + u * rows_per_pass + gi;
-                            v[u] = 1u;
-                            if (active && i < s) {
-                                const double di = (double)i;
-                                const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), jsn);
-                                const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), jcs);
-                                v[u] = fast0 ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0)
-                                             : (inside ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order)
-                                                       : template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order));
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = i0 + u * rows_per_pass + gi;
+                                v[u] = 1u;
+                                if (active && i < s) {
+                                    const double di = (double)i;
+                                    const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), jsn);
+                                    const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), jcs);
+                                    v[u] = sample(row, col);
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = i0 + u * rows_per_pass + gi;
+                                if (active && i < s) {
+                                    tdst[i * tpw * 4] = (unsigned char)v[u];
+                                    lsum += v[u]; lsq += v[u] * v[u]; lzero |= (v[u] == 0);
+                                }
                             }
                         }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int i = i0 + u * rows_per_pass + gi;
-                            if (active && i < s) {
-                                tdst[i * tpw * 4] = (unsigned char)v[u];
-                                lsum += v[u]; lsq += v[u] * v[u]; lzero |= (v[u] == 0);
-                            }
-                        }
-                    }
+                    };
+                    if (fast0) sweep([&](double row, double col) { return template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0); });
+                    else if (inside) sweep([&](double row, double col) { return template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 1); });
+                    else sweep([&](double row, double col) { return template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order); });
                     lsum = __reduce_add_sync(0xffffffffu, lsum);
                     lsq = __reduce_add_sync(0xffffffffu, lsq);
                     lzero = __any_sync(0xffffffffu, lzero);
