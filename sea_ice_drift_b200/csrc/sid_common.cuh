@@ -31,8 +31,9 @@ __device__ __forceinline__ float key_f32(uint32_t k) {
 struct BlockScratch {
     double red[32];
     uint32_t hist[256];
-    uint32_t sel[2];
+    uint32_t sel[4];            // bin, rank inside the bin, population of the bin, candidate counter
     uint32_t wtot[32];
+    uint32_t cand[64];
 };
 
 __device__ __forceinline__ double block_sum(double v, BlockScratch &bs) {
@@ -143,7 +144,7 @@ __device__ float block_select_wide(const float *__restrict__ d, int n, int k, ui
                 uint32_t c = excl;
                 for (int j = 0; j < per; ++j) {
                     const uint32_t h = hist[b0 + j];
-                    if (kk < c + h) { bs.sel[0] = b0 + j; bs.sel[1] = kk - c; break; }
+                    if (kk < c + h) { bs.sel[0] = b0 + j; bs.sel[1] = kk - c; bs.sel[2] = h; bs.sel[3] = 0; break; }
                     c += h;
                 }
             }
@@ -152,6 +153,31 @@ __device__ float block_select_wide(const float *__restrict__ d, int n, int k, ui
         prefix |= bs.sel[0] << shift;
         mask |= (uint32_t)(nbins - 1) << shift;
         kk = bs.sel[1];
+        const uint32_t pop = bs.sel[2];
+        if (pass < 2 && pop <= 64u) {
+            // few elements share the prefix: collect them and rank directly instead of further passes
+            for (int it = 0; it < iters; ++it) {
+                const int i = it * nt + tid;
+                if (i < n) {
+                    const uint32_t key = f32_key(d[i]);
+                    if ((key & mask) == prefix) bs.cand[atomicAdd(&bs.sel[3], 1u)] = key;
+                }
+            }
+            __syncthreads();
+            if (tid < (int)pop) {
+                const uint32_t mine = bs.cand[tid];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < pop; ++j) {
+                    const uint32_t o = bs.cand[j];
+                    rank += (o < mine) || (o == mine && j < (uint32_t)tid);
+                }
+                if (rank == kk) bs.sel[0] = mine;
+            }
+            __syncthreads();
+            const uint32_t key = bs.sel[0];
+            __syncthreads();
+            return key_f32(key);
+        }
         __syncthreads();
     }
     return key_f32(prefix);
@@ -230,6 +256,28 @@ __device__ __noinline__ float ncc_value_call(int corr, uint32_t wsum, double wde
     else if (an < __dmul_rn(t, 1.125)) num = num > 0.0 ? 1.0 : -1.0;
     else num = 0.0;
     return __double2float_rn(num);
+}
+
+// three angles of one output position per call: three independent FP64 chains (ILP), one call overhead
+struct Ncc3 { float v0, v1, v2; };
+__device__ __forceinline__ double ncc_finish(double num, double t) {
+    const double an = fabs(num);
+    if (an < t) return __ddiv_rn(num, t);
+    if (an < __dmul_rn(t, 1.125)) return num > 0.0 ? 1.0 : -1.0;
+    return 0.0;
+}
+__device__ __noinline__ Ncc3 ncc_value_call3(int c0, int c1, int c2, uint32_t wsum, double wden,
+                                             double m0, double n0, double m1, double n1, double m2, double n2) {
+    const double ws = (double)wsum;
+    const double num0 = __dsub_rn((double)c0, __dmul_rn(ws, m0));
+    const double num1 = __dsub_rn((double)c1, __dmul_rn(ws, m1));
+    const double num2 = __dsub_rn((double)c2, __dmul_rn(ws, m2));
+    const double t0 = __dmul_rn(wden, n0), t1 = __dmul_rn(wden, n1), t2 = __dmul_rn(wden, n2);
+    Ncc3 r;
+    r.v0 = __double2float_rn(ncc_finish(num0, t0));
+    r.v1 = __double2float_rn(ncc_finish(num1, t1));
+    r.v2 = __double2float_rn(ncc_finish(num2, t2));
+    return r;
 }
 
 __device__ __forceinline__ float ncc_value(int64_t corr, uint32_t wsum, double wden, const TemplStats &st) {

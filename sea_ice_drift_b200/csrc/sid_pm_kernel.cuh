@@ -295,10 +295,14 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
                         const int idx = y * RW + x;
                         const uint32_t ws = wsum[idx];
                         const double wd = wden[idx];
+                        const int q = 2 * h + e;
+                        const Ncc3 r3 = ncc_value_call3(acc[0][b][q], acc[NBA > 1 ? 1 : 0][b][q], acc[NBA > 2 ? 2 : 0][b][q], ws, wd,
+                                                        S.st[0].mean, S.st[0].norm, S.st[NBA > 1 ? 1 : 0].mean, S.st[NBA > 1 ? 1 : 0].norm,
+                                                        S.st[NBA > 2 ? 2 : 0].mean, S.st[NBA > 2 ? 2 : 0].norm);
+                        const float vv[3] = {r3.v0, r3.v1, r3.v2};
 #pragma unroll
                         for (int a = 0; a < NBA; ++a) {
-                            const float v = S.st[a].flat ? 1.0f
-                                                         : ncc_value_call(acc[a][b][2 * h + e], ws, wd, S.st[a].mean, S.st[a].norm);
+                            const float v = S.st[a].flat ? 1.0f : vv[a];
                             maps[(size_t)S.slot[a] * max_rr + idx] = v;
                             const unsigned long long k2 = peak_key(v, (uint32_t)idx);
                             key[a] = k2 > key[a] ? k2 : key[a];
