@@ -167,10 +167,13 @@ def main_ours(args):
     s, angles = cfg["img_size"], cfg["angles"]
 
     # CPU baseline first (rank 0, N = 1 only): its fork Pool must not inherit a live CUDA context
-    cpu_run = None
+    cpu_run, cpu_extra = None, None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_run = (threads,) + cpu_port_rate([c1, r1, c2, r2, b], img1, img2, s, angles, args.cpu_sample, threads)
+        cpu_extra = {"threads_1": cpu_port_rate([c1, r1, c2, r2, b], img1, img2, s, angles, max(200, args.cpu_sample // 40), 1)[0],
+                     "threads_5_reference_default": cpu_port_rate([c1, r1, c2, r2, b], img1, img2, s, angles,
+                                                                  max(500, args.cpu_sample // 8), 5)[0]}
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this benchmark has no CPU path; use --impl reference)")
@@ -273,7 +276,7 @@ def main_ours(args):
         if cpu_run is not None:
             threads, rate, m, dt, rows, csel = cpu_run
             agree = int((np.nan_to_num(rows[:, :3], nan=-1) == np.nan_to_num(out[csel][:, :3], nan=-1)).all(axis=1).sum())
-            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "other_thread_counts": cpu_extra,
                    "sample": "%d seeded random grid points of the same workload in %.1f s (fork Pool, %d workers); "
                              "%d/%d rows agree with the GPU in position and angle" % (m, dt, threads, agree, m)}
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
