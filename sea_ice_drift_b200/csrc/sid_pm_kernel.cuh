@@ -138,6 +138,8 @@ struct PmShared {
     int slot[PM_MAX_AB];
     int haszero;
     unsigned int point, next;
+    unsigned int tma_for;         // work item whose window was requested during the previous point's tail (else ~0)
+    int nok, nx0, ny0;            // next point: window valid for prefetch, TMA box origin
     float best_r;
     int best_a, best_idx, best_slot;
 };
@@ -328,6 +330,27 @@ __host__ __device__ inline int pm_pick_tx(int RW) {
     return best;
 }
 
+// Search window of one point: img2[int(r2-hws-b):int(r2+hws+b+1), int(c2-hws-b):int(c2+hws+b+1)] with NumPy's
+// clipping of the far end (reference pmlib.py:200-202).  Returns false for windows the reference cannot process.
+__device__ __forceinline__ bool pm_window_rect(const PmArgs &a, double c1, double r1, double c2, double r2, double brd,
+                                               long long &x0, long long &y0, int &W, int &H) {
+    const int s = a.s, hws = s / 2;
+    bool ok = isfinite(c1) && isfinite(r1) && isfinite(c2) && isfinite(r2) && isfinite(brd) &&
+              fabs(c2) < 1e9 && fabs(r2) < 1e9 && fabs(brd) < 1e9;
+    x0 = y0 = 0; W = H = 0;
+    if (!ok) return false;
+    long long y1, x1;
+    y0 = (long long)(r2 - (double)hws - brd);
+    y1 = (long long)(r2 + (double)hws + brd + 1.0);
+    x0 = (long long)(c2 - (double)hws - brd);
+    x1 = (long long)(c2 + (double)hws + brd + 1.0);
+    if (y1 > a.rows2) y1 = a.rows2;      // numpy slicing clips the far end
+    if (x1 > a.cols2) x1 = a.cols2;
+    ok = y0 >= 0 && x0 >= 0 && (y1 - y0) >= s + 1 && (x1 - x0) >= s + 1;
+    H = (int)(y1 - y0); W = (int)(x1 - x0);
+    return ok;
+}
+
 // Scratch footprint of one CTA (bytes): wden f64[rr] | wsum u32[rr] | region, where the region
 // holds the NCC maps and, before any map exists, the horizontal sums hs/hq u32[hrw] each.
 __host__ __device__ inline size_t pm_scratch_bytes(int max_rr, int max_hrw, int ab, bool smth) {
@@ -364,6 +387,7 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
 
     if (tid == 0) {
         S.next = atomicAdd(a.counter, 1u);
+        S.tma_for = 0xffffffffu;
         if (a.tma) mbar_init(&win_bar, 1);
     }
     for (;;) {
@@ -375,25 +399,29 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
         __syncthreads();
         const long long pi = (long long)S.point;
         if (pi >= a.n) break;
+        const bool prefetched = a.tma && S.tma_for == S.point;  // its window is already on the way (or here)
+        if (a.tma && tid == nt - 1) {
+            // the last thread looks one work item ahead so that thread 0 can prefetch its window during this
+            // point's tail (these loads overlap the wait for this point's own window)
+            int nok = 0;
+            const long long pn = (long long)S.next;
+            if (pn < a.n) {
+                const long long q = a.order ? (long long)a.order[pn] : pn;
+                long long nx0, ny0; int nW, nH;
+                if (pm_window_rect(a, a.c1[q], a.r1[q], a.c2fg[q], a.r2fg[q], a.border[q], nx0, ny0, nW, nH)) {
+                    nok = 1; S.nx0 = (int)(nx0 - (nx0 & 15)); S.ny0 = (int)ny0;
+                }
+            }
+            S.nok = nok;
+        }
         const long long pt = a.order ? (long long)a.order[pi] : pi;
         const double c1 = a.c1[pt], r1 = a.r1[pt], c2 = a.c2fg[pt], r2 = a.r2fg[pt], brd = a.border[pt];
         double *o = a.out + 5 * pt;
 
-        // ---- window rectangle: img2[int(r2-hws-b):int(r2+hws+b+1), int(c2-hws-b):int(c2+hws+b+1)]
-        const int hws = s / 2;
-        bool ok = isfinite(c1) && isfinite(r1) && isfinite(c2) && isfinite(r2) && isfinite(brd) &&
-                  fabs(c2) < 1e9 && fabs(r2) < 1e9 && fabs(brd) < 1e9;
-        long long y0 = 0, y1 = 0, x0 = 0, x1 = 0;
-        if (ok) {
-            y0 = (long long)(r2 - (double)hws - brd);
-            y1 = (long long)(r2 + (double)hws + brd + 1.0);
-            x0 = (long long)(c2 - (double)hws - brd);
-            x1 = (long long)(c2 + (double)hws + brd + 1.0);
-            if (y1 > a.rows2) y1 = a.rows2;      // numpy slicing clips the far end
-            if (x1 > a.cols2) x1 = a.cols2;
-            ok = y0 >= 0 && x0 >= 0 && (y1 - y0) >= s + 1 && (x1 - x0) >= s + 1;
-        }
-        const int H = (int)(y1 - y0), W = (int)(x1 - x0);
+        // ---- window rectangle
+        long long x0, y0;
+        int W, H;
+        bool ok = pm_window_rect(a, c1, r1, c2, r2, brd, x0, y0, W, H);
         const int RH = H - s + 1, RW = W - s + 1, RR = RH * RW;
         const int wpw = a.tma ? a.tma_wpw : pm_window_pitch_words(W, IMMA);
         const int xoff = a.tma ? (int)(x0 & 15) : 0;          // byte offset of window column 0 inside a staged row
@@ -401,6 +429,10 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
         const uint32_t *winx = win32 + (xoff >> 2);
         if (ok) ok = RR <= a.max_rr && H * RW <= a.max_hrw &&
                      (H + (IMMA ? PM_IMMA_ROW_SLACK : 0)) * wpw + PM_WIN_SLACK <= a.win_words;
+        if (prefetched) {                                       // always consume the phase of a requested window
+            mbar_wait(&win_bar, win_phase);
+            win_phase ^= 1u;
+        }
         if (!ok) {
             if (tid == 0) {
                 o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
@@ -414,12 +446,16 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
         //         aligned word and takes its right neighbour by shuffle, four rows in flight per warp.
         if (a.tma) {
             if (tid == 0) {
-                mbar_expect_tx(&win_bar, (unsigned)(a.tma_wpw * 4 * a.tma_rows));
-                tma_load_2d(win32, &tmap2, (int)x0 - xoff, (int)y0, &win_bar);   // innermost start must be 16-byte aligned
+                if (!prefetched) {
+                    mbar_expect_tx(&win_bar, (unsigned)(a.tma_wpw * 4 * a.tma_rows));
+                    tma_load_2d(win32, &tmap2, (int)x0 - xoff, (int)y0, &win_bar);   // innermost start must be 16-byte aligned
+                }
                 S.best_r = -INFINITY; S.best_a = -1; S.best_idx = 0; S.best_slot = -1;
             }
-            mbar_wait(&win_bar, win_phase);
-            win_phase ^= 1u;
+            if (!prefetched) {
+                mbar_wait(&win_bar, win_phase);
+                win_phase ^= 1u;
+            }
         } else {
             const int al8 = 8 * (int)(x0 & 3);
             const unsigned char *g = a.img2 + y0 * a.pitch2 + (x0 - (x0 & 3));
@@ -602,7 +638,13 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
             continue;
         }
 
-        // ---- 4. peak statistics and bookkeeping
+        // ---- 4. peak statistics and bookkeeping.  The window buffer is dead from here on: request the next
+        //         point's window now so that the load overlaps the whole tail.
+        if (a.tma && tid == 0 && S.nok) {
+            mbar_expect_tx(&win_bar, (unsigned)(a.tma_wpw * 4 * a.tma_rows));
+            tma_load_2d(win32, &tmap2, S.nx0, S.ny0, &win_bar);
+            S.tma_for = S.next;
+        }
         const int best_slot = S.best_slot, best_idx = S.best_idx;
         const float *best = maps + (size_t)best_slot * a.max_rr;
         float *tmp_a = maps + (size_t)(best_slot == 0 ? 1 : 0) * a.max_rr;
