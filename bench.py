@@ -326,6 +326,32 @@ def main_ours(args):
     return 0
 
 
+class JsonOnlyStdout(object):
+    """Keep stdout clean for the ONE JSON line: while active, file descriptor 1 points at stderr (so banners
+    printed by native libraries such as NCCL's version line go there); the JSON goes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
 if __name__ == "__main__":
     a = parse_args()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
+    import contextlib
+    import io
+    buf = io.StringIO()
+    with JsonOnlyStdout():
+        with contextlib.redirect_stdout(buf):
+            rc = main_reference(a) if a.impl == "reference" else main_ours(a)
+    line = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    if line:
+        print(line[-1], flush=True)
+    sys.exit(rc)

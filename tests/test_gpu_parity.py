@@ -253,3 +253,13 @@ def test_sharded_pattern_matching_over_nccl_two_gpus():
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:]
     assert "== single GPU: True" in res.stdout
+
+
+def test_time_series_of_pairs_through_one_context(gpu_ctx):
+    """BASELINE configs[4] in miniature: several pairs in sequence through one context (the pair buffers
+    are reused); every pair must equal the exact oracle."""
+    for seed in (11, 12, 13):
+        img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=seed, side=900 + 64 * (seed - 11), grid=14)
+        got = gpu_ctx.run_pair(img1, img2, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
+        ref, _ = co.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=cfg["angles"])
+        assert_equals_exact_oracle(got, ref)
