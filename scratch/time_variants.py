@@ -21,7 +21,7 @@ flops = (len(angles) * 2.0 * s * s * (2 * b + 1 + (s % 2 == 0)) ** 2).sum()
 ref = None
 def run(label, env, reps=5):
     global ref
-    for k in ("SID_PM_THREADS", "SID_PM_GLOBAL_SCRATCH", "SID_PM_PATH", "SID_PM_TMA"): os.environ.pop(k, None)
+    for k in ("SID_PM_THREADS", "SID_PM_GLOBAL_SCRATCH", "SID_PM_PATH", "SID_PM_TMA", "SID_PM_SPLIT_TAIL"): os.environ.pop(k, None)
     os.environ.update(env)
     with torch.cuda.stream(stream):
         for _ in range(2): ctx.run_device(n, *ptrs, int(b.max()), s, angles, 0.0, d_out.data_ptr(), d_st.data_ptr())
@@ -37,7 +37,6 @@ def run(label, env, reps=5):
     print("%-34s %8.3f ms  %7.2f Mvec/s  %6.1f TFLOP/s-eq  (%.0f%% of FP32-FMA peak 74.4)  same_as_first=%s" % (
         label, ms, n / ms / 1e3, flops / ms / 1e9, 100 * flops / ms / 1e9 / 74.45, same), flush=True)
 print(name, "points", n, "angles", angles, "s", s, "border", cfg["border"])
-run("imma, smem scratch, TMA", {})
-run("imma, smem scratch, no TMA", {"SID_PM_TMA": "0"})
-run("dp4a, smem scratch, TMA", {"SID_PM_PATH": "dp4a"})
-run("imma, global scratch, TMA", {"SID_PM_GLOBAL_SCRATCH": "1"})
+run("imma, TMA, split tail", {})
+run("imma, TMA, fused tail", {"SID_PM_SPLIT_TAIL": "0"})
+run("dp4a, TMA, split tail", {"SID_PM_PATH": "dp4a"})

@@ -45,10 +45,11 @@ struct sid_ctx {
     long long pitch1 = 0, pitch2 = 0;
     bool have_pair = false;
     // per-call buffers
-    DevBuf pts, order, out, status, angles, scratch, counter, misc;
+    DevBuf pts, order, out, status, angles, scratch, counter, misc, tail_maps, tail_recs;
     void *pin = nullptr;
     size_t pin_cap = 0;
     int attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tail_hint_n = 0;               // total points of the current host call (sizes the tail hand-off once)
     void *encode_tiled = nullptr;            // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
     bool encode_tried = false;
 };
@@ -206,13 +207,17 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         a.tpl_off = 0;
         a.ab = std::min(n_angles, PM_MAX_AB);
     }
+    // Split tail: peak statistics in a second, light kernel when the result map fits its shared memory
+    const bool smth = (flags & SID_HES_SMTH) != 0;
+    bool split_tail = pm_tail_smem_bytes(a.max_rr, smth) <= 48 * 1024;
+    if (const char *e = getenv("SID_PM_SPLIT_TAIL")) if (e[0] == '0') split_tail = false;
     // Shared memory: window + templates (+ the per-point scratch when it all fits in a third of an SM).
     const size_t smem_cap_fast = 75 * 1024;
     auto base_smem = [&](int ab) { return ((size_t)a.win_words + (size_t)ab * s * a.tpw) * 4; };
     bool smem_scratch = false;
     size_t smem = 0;
     for (int ab = a.ab; ab >= 1 && !smem_scratch; --ab) {
-        const size_t need = base_smem(ab) + pm_scratch_bytes(a.max_rr, a.max_hrw, ab, (flags & SID_HES_SMTH) != 0);
+        const size_t need = base_smem(ab) + pm_scratch_bytes(a.max_rr, a.max_hrw, ab, smth, split_tail);
         // fewer resident templates only pays if it keeps all angles in <= the same number of batches
         if (need <= smem_cap_fast && (n_angles + ab - 1) / ab == (n_angles + a.ab - 1) / a.ab) {
             smem_scratch = true; a.ab = ab; smem = need;
@@ -270,7 +275,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     if (grid > n) grid = n;
     if (grid < 1) grid = 1;
 
-    a.scratch_per_cta = pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab, (flags & SID_HES_SMTH) != 0);
+    a.scratch_per_cta = pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab, smth, split_tail);
     int rc = SID_OK;
     if (!smem_scratch) {
         rc = reserve(ctx, ctx->scratch, (size_t)a.scratch_per_cta * (size_t)grid);
@@ -282,9 +287,23 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     a.counter = (unsigned int *)ctx->counter.p;
     CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
 
+    a.split_tail = split_tail ? 1 : 0;
+    if (split_tail) {
+        const size_t cap_n = (size_t)std::max<long long>(n, ctx->tail_hint_n);
+        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.max_rr * sizeof(float)))) return rc;
+        if ((rc = reserve(ctx, ctx->tail_recs, cap_n * sizeof(PmTailRec)))) return rc;
+        a.tail_maps = (float *)ctx->tail_maps.p;
+        a.tail_recs = (PmTailRec *)ctx->tail_recs.p;
+    }
     void *params[] = {(void *)&a, (void *)&tmap};
     CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, ctx->stream));
     ctx->launches += 1;
+    if (split_tail) {
+        const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
+        pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, ctx->stream>>>(a);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+    }
     return SID_OK;
 }
 
@@ -321,7 +340,7 @@ void sid_destroy(sid_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->img1, &ctx->img2, &ctx->pts, &ctx->order, &ctx->out, &ctx->status,
-                      &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc};
+                      &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->copy_stream) {
@@ -521,6 +540,8 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
 
 
     const double *dp = (const double *)ctx->pts.p;
+    ctx->tail_hint_n = 0;
+    for (int k = 0; k < nbands; ++k) ctx->tail_hint_n = std::max<long long>(ctx->tail_hint_n, band_start[(size_t)k + 1] - band_start[(size_t)k]);
     for (int k = 0; k < nbands; ++k) {
         if (pair) CU(cudaStreamWaitEvent(ctx->stream, ctx->band_event[k], 0));
         const int lo = band_start[(size_t)k], hi = band_start[(size_t)k + 1];

@@ -35,6 +35,16 @@ constexpr int PM_SEG = 16;        // outputs per horizontal sliding-sum work ite
 constexpr int PM_VSEG = 8;        // outputs per vertical sliding-sum work item
 constexpr int PM_WIN_SLACK = 64;  // words readable past the staged window
 
+// Hand-off from the fused kernel to pm_tail_kernel (one record per work item of the launch).
+struct PmTailRec {
+    int pt;            // point index, or -1 when the fused kernel already wrote the (NaN) row
+    int RH, RW;        // result map shape
+    int H, W;          // window shape (for the displacement bookkeeping)
+    int best_idx;      // flat index of the peak
+    int best_a;        // index of the winning angle
+    float best_r;      // peak value
+};
+
 struct PmArgs {
     const uint8_t *img1; int rows1, cols1; long long pitch1;
     const uint8_t *img2; int rows2, cols2; long long pitch2;
@@ -63,6 +73,11 @@ struct PmArgs {
     int tma;                      // 1: stage the window with a TMA 2-D tile load (box = tma_wpw*4 x tma_rows bytes)
     int tma_wpw, tma_rows;
     unsigned int *counter;        // work-stealing cursor
+    // split tail (small result maps): the fused kernel stores the winning map + a record per work item and
+    // pm_tail_kernel computes the peak statistics at much higher occupancy
+    int split_tail;
+    float *tail_maps;             // n x max_rr
+    PmTailRec *tail_recs;         // n
 };
 
 __host__ __device__ inline int pm_window_pitch_words(int W, bool imma = false) {
@@ -353,10 +368,10 @@ __device__ __forceinline__ bool pm_window_rect(const PmArgs &a, double c1, doubl
 
 // Scratch footprint of one CTA (bytes): wden f64[rr] | wsum u32[rr] | region, where the region
 // holds the NCC maps and, before any map exists, the horizontal sums hs/hq u32[hrw] each.
-__host__ __device__ inline size_t pm_scratch_bytes(int max_rr, int max_hrw, int ab, bool smth) {
+__host__ __device__ inline size_t pm_scratch_bytes(int max_rr, int max_hrw, int ab, bool smth, bool split_tail = false) {
     // maps: ab + 1 angle slots (one always keeps the best so far), the Hessian map, and a second
-    // smoothing temporary only when hes_smth is requested
-    size_t maps = (size_t)(ab + 2 + (smth ? 1 : 0)) * max_rr * 4, hsq = (size_t)max_hrw * 8;
+    // smoothing temporary only when hes_smth is requested; none of the latter two with a split tail
+    size_t maps = (size_t)(ab + 1 + (split_tail ? 0 : 1 + (smth ? 1 : 0))) * max_rr * 4, hsq = (size_t)max_hrw * 8;
     size_t b = (size_t)max_rr * 12 + (maps > hsq ? maps : hsq);
     return (b + 255) & ~(size_t)255;
 }
@@ -437,6 +452,7 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
             if (tid == 0) {
                 o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
                 if (a.status) a.status[pt] = -1;
+                if (a.split_tail) a.tail_recs[pi].pt = -1;
             }
             continue;
         }
@@ -634,6 +650,7 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
             if (tid == 0) {
                 o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
                 if (a.status) a.status[pt] = 0;
+                if (a.split_tail) a.tail_recs[pi].pt = -1;
             }
             continue;
         }
@@ -647,6 +664,18 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
         }
         const int best_slot = S.best_slot, best_idx = S.best_idx;
         const float *best = maps + (size_t)best_slot * a.max_rr;
+        if (a.split_tail) {
+            // hand the winning map to pm_tail_kernel and move on to the next point
+            float *dst = a.tail_maps + (size_t)pi * a.max_rr;
+            for (int k = tid; k < RR; k += nt) dst[k] = best[k];
+            if (tid == 0) {
+                PmTailRec rec;
+                rec.pt = (int)pt; rec.RH = RH; rec.RW = RW; rec.H = H; rec.W = W;
+                rec.best_idx = best_idx; rec.best_a = S.best_a; rec.best_r = S.best_r;
+                a.tail_recs[pi] = rec;
+            }
+            continue;
+        }
         float *tmp_a = maps + (size_t)(best_slot == 0 ? 1 : 0) * a.max_rr;
         float *hes = maps + (size_t)(ab + 1) * a.max_rr;
         float *tmp_b = maps + (size_t)(ab + 2) * a.max_rr;      // only allocated (and touched) with hes_smth
@@ -667,5 +696,38 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
     }
 }
 
+// Peak statistics of one work item per CTA (reference pmlib.py:167-172, 209-210) on the map the fused kernel
+// handed over.  Light on registers and shared memory, so ~10 CTAs are resident per SM.
+constexpr int PM_TAIL_THREADS = 128;
+__global__ void __launch_bounds__(PM_TAIL_THREADS) pm_tail_kernel(const PmArgs a) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    __shared__ BlockScratch bs;
+    const PmTailRec rec = a.tail_recs[blockIdx.x];
+    if (rec.pt < 0) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int RR = rec.RH * rec.RW;
+    float *map = reinterpret_cast<float *>(tail_smem);
+    float *hes = map + a.max_rr;
+    uint32_t *wide_hist = reinterpret_cast<uint32_t *>(hes + a.max_rr);
+    float *tmp_a = reinterpret_cast<float *>(wide_hist + 2048);        // only with hes_smth
+    float *tmp_b = tmp_a + a.max_rr;
+    const float *src = a.tail_maps + (size_t)blockIdx.x * a.max_rr;
+    for (int k = tid; k < RR; k += nt) map[k] = src[k];
+    __syncthreads();
+    const PeakStats ps = peak_statistics(map, rec.RH, rec.RW, rec.best_idx, rec.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, bs, wide_hist);
+    if (tid == 0) {
+        const int bi = rec.best_idx / rec.RW, bj = rec.best_idx - bi * rec.RW;
+        const double dr = (double)bi - (double)(rec.H - a.s) / 2.0;
+        const double dc = (double)bj - (double)(rec.W - a.s) / 2.0;
+        double *o = a.out + 5 * (long long)rec.pt;
+        o[0] = a.c2fg[rec.pt] + dc;
+        o[1] = a.r2fg[rec.pt] + dr;
+        o[2] = a.angles[rec.best_a];
+        o[3] = (double)ps.r;
+        o[4] = (double)ps.h;
+        if (a.status) a.status[rec.pt] = 1;
+    }
+}
+inline size_t pm_tail_smem_bytes(int max_rr, bool smth) { return (size_t)max_rr * 4 * (2 + (smth ? 2 : 0)) + 2048 * 4; }
 
 }  // namespace sid

@@ -2,7 +2,7 @@
 They mirror the reference's helper names (reference sea_ice_drift/lib.py:139-201,
 408-412) so that callers can switch imports; none of them is on the hot path."""
 import numpy as np
-from scipy.interpolate import griddata
+from scipy.interpolate import griddata, LinearNDInterpolator
 
 
 def _poly_design(x, y, order):
@@ -31,6 +31,11 @@ def interpolation_near(x1, y1, x2, y2, x1grd, y1grd, method='linear', **kwargs):
     the convex hull of the keypoints (reference lib.py:179-201)."""
     src = np.array([y1, x1]).T
     dst = np.array([y1grd, x1grd]).T
+    if method == 'linear' and src.ndim == 2 and src.shape[1] == 2:
+        # what griddata(method='linear') does, but with ONE Delaunay triangulation shared by both value
+        # sets (the reference triangulates the same keypoints twice); values are identical
+        both = LinearNDInterpolator(src, np.column_stack([x2, y2]), fill_value=np.nan)(dst)
+        return both[:, 0].T, both[:, 1].T
     return (griddata(src, x2, dst, method=method).T,
             griddata(src, y2, dst, method=method).T)
 
