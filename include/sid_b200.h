@@ -126,6 +126,9 @@ int sid_run_device(sid_ctx *ctx, int64_t n,
 
 /* Number of kernel launches issued by this context so far (bench accounting). */
 int64_t sid_launch_count(const sid_ctx *ctx);
+/* Device time (ms, CUDA events on the launching stream) of the most recent launch of the fused
+ * point kernel; waits for it to finish.  -1 if nothing was launched yet. */
+double sid_last_kernel_ms(sid_ctx *ctx);
 
 /* rotate_and_match for one point against an explicit search window `image2`
  * (host pointers).  Outputs: *valid (0 -> the reference returns 7 x NaN),

@@ -49,6 +49,8 @@ struct sid_ctx {
     void *pin = nullptr;
     size_t pin_cap = 0;
     int attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t k_ev[2] = {};                // bracket the last fused-kernel launch (sid_last_kernel_ms)
+    bool k_ev_valid = false;
     long long tail_hint_n = 0;               // total points of the current host call (sizes the tail hand-off once)
     void *encode_tiled = nullptr;            // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
     bool encode_tried = false;
@@ -296,7 +298,11 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         a.tail_recs = (PmTailRec *)ctx->tail_recs.p;
     }
     void *params[] = {(void *)&a, (void *)&tmap};
+    if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
+    CU(cudaEventRecord(ctx->k_ev[0], ctx->stream));
     CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, ctx->stream));
+    CU(cudaEventRecord(ctx->k_ev[1], ctx->stream));
+    ctx->k_ev_valid = true;
     ctx->launches += 1;
     if (split_tail) {
         const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
@@ -343,6 +349,7 @@ void sid_destroy(sid_ctx *ctx) {
                       &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    for (cudaEvent_t e : ctx->k_ev) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) {
         cudaStreamDestroy(ctx->copy_stream);
         for (cudaEvent_t e : ctx->band_event) if (e) cudaEventDestroy(e);
@@ -367,6 +374,16 @@ int sid_synchronize(sid_ctx *ctx) {
 }
 
 int64_t sid_launch_count(const sid_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+double sid_last_kernel_ms(sid_ctx *ctx) {
+    if (!ctx || !ctx->k_ev_valid) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->k_ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->k_ev[0], ctx->k_ev[1]) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.0;
+    }
+    return (double)ms;
+}
 
 static int set_pair_impl(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
                          const uint8_t *img2, int rows2, int cols2, int64_t pitch2, cudaMemcpyKind kind) {
