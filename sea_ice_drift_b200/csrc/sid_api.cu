@@ -36,6 +36,8 @@ struct sid_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // image upload, overlapped with compute (sid_run_pair)
+    cudaStream_t band_stream[2] = {nullptr, nullptr};   // band launches alternate here so their tails overlap
+    cudaEvent_t slot_event[3] = {};          // points uploaded, band stream 0 done, band stream 1 done
     cudaEvent_t band_event[17] = {};
     std::string err;
     long long launches = 0;
@@ -156,7 +158,9 @@ bool make_window_tensor_map(sid_ctx *ctx, CUtensorMap *map, int box_w, int box_h
 int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1, const double *d_c2fg,
               const double *d_r2fg, const double *d_border, const int *d_order, int max_border, int typ_border,
               int img_size, int n_angles, const double *d_angles, const double *d_tab, int rot_order,
-              unsigned flags, double *d_out, int *d_status) {
+              unsigned flags, double *d_out, int *d_status,
+              cudaStream_t st = nullptr, int slot = 0, long long tail_off = 0) {
+    if (!st) st = ctx->stream;
     const int s = img_size;
     const int hws = s / 2;
     const int Wmax = 2 * hws + 2 * max_border + 1;
@@ -280,33 +284,34 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     a.scratch_per_cta = pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab, smth, split_tail);
     int rc = SID_OK;
     if (!smem_scratch) {
-        rc = reserve(ctx, ctx->scratch, (size_t)a.scratch_per_cta * (size_t)grid);
+        const size_t per_slot = (size_t)a.scratch_per_cta * (size_t)ctx->sm_count * (size_t)occ;
+        rc = reserve(ctx, ctx->scratch, per_slot * 2);
         if (rc) return rc;
-        a.scratch = (unsigned char *)ctx->scratch.p;
+        a.scratch = (unsigned char *)ctx->scratch.p + per_slot * (size_t)slot;
     }
     rc = reserve(ctx, ctx->counter, 256);
     if (rc) return rc;
-    a.counter = (unsigned int *)ctx->counter.p;
-    CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), ctx->stream));
+    a.counter = (unsigned int *)ctx->counter.p + 16 * slot;
+    CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
 
     a.split_tail = split_tail ? 1 : 0;
     if (split_tail) {
-        const size_t cap_n = (size_t)std::max<long long>(n, ctx->tail_hint_n);
+        const size_t cap_n = (size_t)std::max<long long>(n + tail_off, ctx->tail_hint_n);
         if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.max_rr * sizeof(float)))) return rc;
         if ((rc = reserve(ctx, ctx->tail_recs, cap_n * sizeof(PmTailRec)))) return rc;
-        a.tail_maps = (float *)ctx->tail_maps.p;
-        a.tail_recs = (PmTailRec *)ctx->tail_recs.p;
+        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.max_rr;
+        a.tail_recs = (PmTailRec *)ctx->tail_recs.p + tail_off;
     }
     void *params[] = {(void *)&a, (void *)&tmap};
     if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
-    CU(cudaEventRecord(ctx->k_ev[0], ctx->stream));
-    CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, ctx->stream));
-    CU(cudaEventRecord(ctx->k_ev[1], ctx->stream));
+    CU(cudaEventRecord(ctx->k_ev[0], st));
+    CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, st));
+    CU(cudaEventRecord(ctx->k_ev[1], st));
     ctx->k_ev_valid = true;
     ctx->launches += 1;
     if (split_tail) {
         const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
-        pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, ctx->stream>>>(a);
+        pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, st>>>(a);
         ctx->launches += 1;
         CU(cudaGetLastError());
     }
@@ -350,6 +355,8 @@ void sid_destroy(sid_ctx *ctx) {
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     for (cudaEvent_t e : ctx->k_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->slot_event) if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : ctx->band_stream) if (st) cudaStreamDestroy(st);
     if (ctx->copy_stream) {
         cudaStreamDestroy(ctx->copy_stream);
         for (cudaEvent_t e : ctx->band_event) if (e) cudaEventDestroy(e);
@@ -557,16 +564,32 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
 
 
     const double *dp = (const double *)ctx->pts.p;
-    ctx->tail_hint_n = 0;
-    for (int k = 0; k < nbands; ++k) ctx->tail_hint_n = std::max<long long>(ctx->tail_hint_n, band_start[(size_t)k + 1] - band_start[(size_t)k]);
+    ctx->tail_hint_n = n;
+    const bool two_streams = pair && nbands > 1;
+    if (two_streams) {
+        if (!ctx->band_stream[0]) {
+            for (int k = 0; k < 2; ++k) CU(cudaStreamCreateWithFlags(&ctx->band_stream[k], cudaStreamNonBlocking));
+            for (int k = 0; k < 3; ++k) CU(cudaEventCreateWithFlags(&ctx->slot_event[k], cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(ctx->slot_event[0], ctx->stream));            // point / angle uploads are enqueued
+        for (int k = 0; k < 2; ++k) CU(cudaStreamWaitEvent(ctx->band_stream[k], ctx->slot_event[0], 0));
+    }
     for (int k = 0; k < nbands; ++k) {
-        if (pair) CU(cudaStreamWaitEvent(ctx->stream, ctx->band_event[k], 0));
+        // consecutive bands go to alternating streams: the next band's CTAs fill the SMs while this one drains
+        cudaStream_t st = two_streams ? ctx->band_stream[k & 1] : ctx->stream;
+        if (pair) CU(cudaStreamWaitEvent(st, ctx->band_event[k], 0));
         const int lo = band_start[(size_t)k], hi = band_start[(size_t)k + 1];
         if (hi <= lo) continue;
         rc = launch_pm(ctx, hi - lo, dp, dp + n, dp + 2 * n, dp + 3 * n, dp + 4 * n, (const int *)ctx->order.p + lo,
                        max_border, typ_border, img_size, n_angles, d_angles, d_tab, rot_order, flags,
-                       (double *)ctx->out.p, (int *)ctx->status.p);
+                       (double *)ctx->out.p, (int *)ctx->status.p, st, two_streams ? (k & 1) : 0, lo);
         if (rc) return rc;
+    }
+    if (two_streams) {
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaEventRecord(ctx->slot_event[1 + k], ctx->band_stream[k]));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->slot_event[1 + k], 0));
+        }
     }
     if (pair) ctx->have_pair = true;
     double *hout = (double *)((char *)ctx->pin + pts_bytes + ord_bytes);

@@ -154,6 +154,9 @@ def test_edge_cases_and_errors(gpu_ctx, golden_points):
     gpu_ctx.set_pair(g["img1"], g["img2"])
     out = gpu_ctx.run([], [], [], [], [], 35, [0], 0.0)
     assert out.shape == (0, 5)
+    before = gpu_ctx.launch_count
+    gpu_ctx.run([100.0], [100.0], [100.0], [100.0], [20.0], 35, [0], 0.0)
+    assert gpu_ctx.launch_count > before and 0.0 < gpu_ctx.last_kernel_ms < 1000.0
     out, st = gpu_ctx.run([245.0, 100.0, 100.0, np.nan], [160.0, 100.0, 100.0, 100.0], [245.0, 10.0, 100.0, 100.0],
                           [160.0, 100.0, 100.0, 100.0], [20.0, 20.0, 20.0, 20.0], 35, [-3, 0, 3], 0.0, want_status=True)
     assert st.tolist() == [0, -1, 1, -1]
