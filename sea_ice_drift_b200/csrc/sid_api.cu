@@ -50,7 +50,6 @@ struct sid_ctx {
     DevBuf pts, order, out, status, angles, scratch, counter, misc, tail_maps, tail_recs;
     void *pin = nullptr;
     size_t pin_cap = 0;
-    int attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t k_ev[2] = {};                // bracket the last fused-kernel launch (sid_last_kernel_ms)
     bool k_ev_valid = false;
     long long tail_hint_n = 0;               // total points of the current host call (sizes the tail hand-off once)
@@ -75,6 +74,17 @@ int cuda_fail(sid_ctx *c, cudaError_t e, const char *what) {
         cudaError_t e_ = (call);                                   \
         if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-process, per-device property of the kernel (not of a
+// context): raise it to the device's opt-in maximum, and re-assert it whenever some other context may have
+// changed it -- setting it is cheap and idempotent.
+int allow_max_smem(sid_ctx *ctx, const void *kernel) {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kernel));
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            ctx->max_smem_optin - (int)fa.sharedSizeBytes));
+    return SID_OK;
+}
 
 int reserve(sid_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return SID_OK;
@@ -215,7 +225,8 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     }
     // Split tail: peak statistics in a second, light kernel when the result map fits its shared memory
     const bool smth = (flags & SID_HES_SMTH) != 0;
-    bool split_tail = pm_tail_smem_bytes(a.max_rr, smth) <= 48 * 1024;
+    bool split_tail = pm_tail_smem_bytes(a.max_rr, smth) <= 52 * 1024;       // >= 4 tail CTAs per SM; larger maps measured
+                                                                             // faster with the fused tail (cfg1: 1.10 vs 1.21 ms)
     if (const char *e = getenv("SID_PM_SPLIT_TAIL")) if (e[0] == '0') split_tail = false;
     // Shared memory: window + templates (+ the per-point scratch when it all fits in a third of an SM).
     const size_t smem_cap_fast = 75 * 1024;
@@ -270,13 +281,15 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
                            (const void *)pm_points_kernel<0, false, true>, (const void *)pm_points_kernel<0, true, true>};
     const int kidx = imma ? (smem_scratch ? 7 : 6) : variant + (smem_scratch ? 3 : 0);
     const void *kfn = ktab[kidx];
-    if (ctx->attr_smem[kidx] < (int)smem) {
-        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
-        ctx->attr_smem[kidx] = (int)std::max(smem, (size_t)49152);
-    }
+    if (int arc = allow_max_smem(ctx, kfn)) return arc;
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
-    if (occ < 1) return fail(ctx, SID_ECUDA, "kernel does not fit on an SM");
+    if (occ < 1) {
+        char msg[256];
+        snprintf(msg, sizeof msg, "kernel does not fit on an SM (variant %d, %d threads, %zu B dynamic smem, img_size %d, max border %d, "
+                 "%d angles/batch, tma %d)", kidx, threads, smem, s, max_border, a.ab, a.tma);
+        return fail(ctx, SID_ECUDA, msg);
+    }
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > n) grid = n;
     if (grid < 1) grid = 1;
@@ -311,6 +324,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     ctx->launches += 1;
     if (split_tail) {
         const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
+        if (int arc = allow_max_smem(ctx, (const void *)pm_tail_kernel)) return arc;
         pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, st>>>(a);
         ctx->launches += 1;
         CU(cudaGetLastError());
@@ -700,7 +714,7 @@ static int match_on_device(sid_ctx *ctx, const uint8_t *d_img, int H, int W, lon
     a.wpw = n16 * 4;
     const size_t smem = ((size_t)(MT_ROWS + th - 1) * a.wpw + PM_WIN_SLACK + (size_t)th * a.tpw) * 4;
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SID_EUNSUPPORTED, "template too large for match_template");
-    CU(cudaFuncSetAttribute(match_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+    if (int arc = allow_max_smem(ctx, (const void *)match_template_kernel)) return arc;
     dim3 grid((RW + MT_COLS - 1) / MT_COLS, (RH + MT_ROWS - 1) / MT_ROWS);
     match_template_kernel<<<grid, 256, smem, ctx->stream>>>(a);
     ctx->launches += 2;

@@ -266,3 +266,40 @@ def test_time_series_of_pairs_through_one_context(gpu_ctx):
         got = gpu_ctx.run_pair(img1, img2, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
         ref, _ = co.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=cfg["angles"])
         assert_equals_exact_oracle(got, ref)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_randomised_configurations_equal_exact_oracle(gpu_ctx, seed):
+    """Random image shapes (not multiples of 16), template sizes, per-point borders, angle lists, alpha0 and
+    option flags, with points pushed against every image edge (far-edge windows are clipped like NumPy
+    slices, near-edge ones rejected) -- everything must equal the exact CPU oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    rows, cols = int(rng.integers(300, 700)), int(rng.integers(300, 700))
+    img1 = syn.speckle_image((rows, cols), seed=seed)
+    m = syn.rotation_matrix((rows, cols), float(rng.uniform(-3, 3)))
+    m[0, 2] += rng.uniform(-6, 6)
+    m[1, 2] += rng.uniform(-6, 6)
+    img2 = syn.warp_pair(img1, m, seed=seed)
+    if seed % 3 == 0:
+        img1 = img1.copy()
+        img1[rows // 3: rows // 3 + 25, cols // 2: cols // 2 + 30] = 0
+    s = int(rng.choice([5, 8, 17, 24, 33, 35, 36, 41, 50, 51, 64]))
+    n = 60
+    bmax = int(rng.integers(3, 45))
+    brd = np.floor(rng.uniform(max(1, bmax // 3), bmax + 1, n))
+    c1 = rng.uniform(0, cols, n)
+    r1 = rng.uniform(0, rows, n)
+    tx, ty = syn.apply_affine(m, c1, r1)
+    c2 = np.round(tx + rng.normal(0, 2, n))
+    r2 = np.round(ty + rng.normal(0, 2, n))
+    c2[:6] = [3, cols - 3, cols // 2, cols // 2, cols - s // 2 - 2, s]           # hug the edges
+    r2[:6] = [rows // 2, rows // 2, 2, rows - 2, rows - s // 2 - 2, rows - s]
+    angles = sorted(set(np.round(rng.uniform(-12, 12, int(rng.integers(1, 8))), 1).tolist()))
+    alpha0 = float(rng.uniform(-5, 5))
+    opts = dict(rot_order=int(rng.integers(0, 2)), hes_norm=bool(rng.integers(0, 2)),
+                hes_smth=bool(rng.integers(0, 2)), mcc_norm=bool(rng.integers(0, 2)))
+    pts = [c1, r1, c2, r2, brd]
+    got, st = gpu_ctx.run_pair(img1, img2, *pts, s, angles, alpha0, opts["rot_order"], flags(opts), want_status=True)
+    ref, st2 = co.use_mcc_batch(*pts, img1, img2, s, alpha0, angles=angles, **opts)
+    assert_equals_exact_oracle(got, ref, st, st2)
+    assert (st == 1).sum() >= 5
