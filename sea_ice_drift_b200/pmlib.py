@@ -41,7 +41,8 @@ def _ctx(kwargs=None):
 def _pair_fingerprint(img):
     a = np.asarray(img)
     step = max(1, a.size // 4096)
-    return (a.__array_interface__['data'][0], a.shape, a.strides, int(a.reshape(-1)[::step].sum(dtype=np.int64)))
+    # .flat[::step] visits only the sampled elements (reshape(-1) would copy a non-contiguous view)
+    return (a.__array_interface__['data'][0], a.shape, a.strides, int(a.flat[::step].sum(dtype=np.int64)))
 
 
 def _ensure_pair(ctx, img1, img2):

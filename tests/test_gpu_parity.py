@@ -303,3 +303,43 @@ def test_randomised_configurations_equal_exact_oracle(gpu_ctx, seed):
     ref, st2 = co.use_mcc_batch(*pts, img1, img2, s, alpha0, angles=angles, **opts)
     assert_equals_exact_oracle(got, ref, st, st2)
     assert (st == 1).sum() >= 5
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_single_call_api_equals_exact_oracle(gpu_ctx, seed):
+    rng = np.random.default_rng(2000 + seed)
+    img = syn.speckle_image((int(rng.integers(120, 400)), int(rng.integers(120, 400))), seed=50 + seed)
+    # template_matcher plug-in: non-square templates, image sizes not multiples of the tile
+    th, tw = int(rng.integers(3, 70)), int(rng.integers(3, 70))
+    H, W = int(rng.integers(th, img.shape[0] + 1)), int(rng.integers(tw, img.shape[1] + 1))
+    y, x = int(rng.integers(0, img.shape[0] - H + 1)), int(rng.integers(0, img.shape[1] - W + 1))
+    win = img[y:y + H, x:x + W]
+    ty, tx = int(rng.integers(0, img.shape[0] - th + 1)), int(rng.integers(0, img.shape[1] - tw + 1))
+    tpl = img[ty:ty + th, tx:tx + tw]
+    assert np.array_equal(gpu_ctx.match_template(win, tpl),
+                          co.match_template(np.ascontiguousarray(win), np.ascontiguousarray(tpl)))
+    # get_hessian on maps of any shape >= 2 x 2
+    rows, cols = int(rng.integers(2, 90)), int(rng.integers(2, 90))
+    ccm = rng.normal(0, 0.3, (rows, cols)).astype(np.float32)
+    for hn in (False, True):
+        for hs in (False, True):
+            got = gpu_ctx.get_hessian(ccm, _lib.flags_from_kwargs(hn, hs, False))
+            ref = co.get_hessian(ccm, hes_norm=hn, hes_smth=hs)
+            assert np.all(np.abs(got - ref) <= 4e-6 * (1 + np.abs(ref))), (rows, cols, hn, hs)
+    # get_template anywhere, including partly outside the image
+    for order in (0, 1):
+        c, r, ang, s = rng.uniform(-10, img.shape[1] + 10), rng.uniform(-10, img.shape[0] + 10), rng.uniform(-180, 180), int(rng.integers(3, 80))
+        assert np.array_equal(gpu_ctx.get_template(img, c, r, ang, s, order), co.get_template(img, c, r, ang, s, rot_order=order))
+    # rotate_and_match against an explicit, non-square window
+    s = int(rng.integers(5, 60))
+    Hh, Ww = int(rng.integers(s + 2, s + 60)), int(rng.integers(s + 2, s + 60))
+    img2 = syn.speckle_image((Hh, Ww), seed=90 + seed)
+    angles = sorted(set(np.round(rng.uniform(-10, 10, int(rng.integers(1, 6))), 1).tolist()))
+    c, r = rng.uniform(s, img.shape[1] - s), rng.uniform(s, img.shape[0] - s)
+    kw = dict(rot_order=int(rng.integers(0, 2)), hes_norm=bool(rng.integers(0, 2)), hes_smth=bool(rng.integers(0, 2)))
+    mcc = bool(rng.integers(0, 2))
+    got = sid.rotate_and_match(img, c, r, s, img2, 1.1, angles=angles, mcc_norm=mcc, **kw)
+    ref = co.rotate_and_match(img, c, r, s, img2, 1.1, angles=angles, mcc_norm=mcc, **kw)
+    assert got[:3] == ref[:3]
+    assert abs(got[3] - ref[3]) <= 4e-6 * (1 + abs(ref[3])) and abs(got[4] - ref[4]) <= 4e-6 * (1 + abs(ref[4]))
+    assert np.array_equal(got[5], ref[5]) and np.array_equal(got[6], ref[6])
