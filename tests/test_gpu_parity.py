@@ -343,3 +343,17 @@ def test_randomised_single_call_api_equals_exact_oracle(gpu_ctx, seed):
     assert got[:3] == ref[:3]
     assert abs(got[3] - ref[3]) <= 4e-6 * (1 + abs(ref[3])) and abs(got[4] - ref[4]) <= 4e-6 * (1 + abs(ref[4]))
     assert np.array_equal(got[5], ref[5]) and np.array_equal(got[6], ref[6])
+
+
+def test_image_narrower_than_tma_box_and_corner_windows(gpu_ctx):
+    """The TMA box (window width rounded up + 15 bytes) can be wider than the whole image and can hang over the
+    right / bottom edges: out-of-image bytes must read as zeros and never fault."""
+    img1 = syn.speckle_image((88, 85), seed=3)
+    img2 = syn.warp_pair(img1, syn.shift_matrix(1.0, -1.0), seed=3)
+    c = np.array([42.0, 45.0, 46.3]); r = np.array([44.0, 47.0, 48.6])
+    c2 = np.array([42.0, 46.0, 47.0]); r2 = np.array([44.0, 49.0, 50.0])
+    b = np.array([20.0, 20.0, 20.0])
+    got, st = gpu_ctx.run_pair(img1, img2, c, r, c2, r2, b, 35, [-3, 0, 3], 0.0, want_status=True)
+    ref, st2 = co.use_mcc_batch(c, r, c2, r2, b, img1, img2, 35, 0.0, angles=[-3, 0, 3])
+    assert_equals_exact_oracle(got, ref, st, st2)
+    assert (st == 1).sum() >= 1
