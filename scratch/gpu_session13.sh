@@ -2,6 +2,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu_info.txt
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.txt; tail -3 gpurun_out/pytest_gpu.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; cat gpurun_out/smoke.txt | tail -2
 timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1_err.txt; echo "rc=$?" >> gpurun_out/bench_n1_err.txt
 timeout 600 python bench.py --impl reference --steps 10 --warmup 1 > gpurun_out/bench_ref_n1.json 2> gpurun_out/bench_ref_err.txt
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2_err.txt; echo "rc=$?" >> gpurun_out/bench_n2_err.txt
