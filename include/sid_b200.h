@@ -157,6 +157,15 @@ int sid_match_template(sid_ctx *ctx,
                        const uint8_t *tpl, int th, int tw, int64_t tpitch,
                        int method, float *out);
 
+/* Feature-tracking matcher (the caller side of the hot path): the two nearest train descriptors
+ * in Hamming distance for every query descriptor, i.e. what
+ * cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d1, d2, k=2) returns at the reference's call site
+ * ftlib.py:92-99 (the `matcher` plug-in kwarg of get_match_coords).  Host pointers, descriptors are rows of
+ * desc_bytes bytes (32 = ORB).  idx / dist: n1 x 2 ints, best first; equal distances go to the lower train
+ * index (OpenCV's order); -1 where fewer than two train descriptors exist. */
+int sid_knn_hamming2(sid_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int desc_bytes,
+                     int32_t *idx, int32_t *dist);
+
 /* get_hessian of a float32 map (rows x cols) -> float32 map of the same shape. */
 int sid_get_hessian(sid_ctx *ctx, const float *ccm, int rows, int cols,
                     unsigned flags, float *out);

@@ -136,3 +136,16 @@ def use_mcc_batch(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, angl
         if rc:
             raise ValueError("sido_use_mcc_batch rc=%d" % rc)
     return out, status
+
+
+def knn_hamming2(d1, d2):
+    """Two nearest train descriptors per query, OpenCV ordering (reference ftlib.py:95-96)."""
+    d1 = np.ascontiguousarray(d1, dtype=np.uint8)
+    d2 = np.ascontiguousarray(d2, dtype=np.uint8)
+    idx = np.full((d1.shape[0], 2), -1, np.int32)
+    dist = np.full((d1.shape[0], 2), -1, np.int32)
+    rc = lib().sido_knn_hamming2(_ptr(d1, _u8p), C.c_int(d1.shape[0]), _ptr(d2, _u8p), C.c_int(d2.shape[0]),
+                                 C.c_int(d1.shape[1]), _ptr(idx, _i32p), _ptr(dist, _i32p))
+    if rc:
+        raise ValueError("sido_knn_hamming2 rc=%d" % rc)
+    return idx, dist

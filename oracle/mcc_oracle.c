@@ -413,3 +413,25 @@ int sido_use_mcc_batch(int64_t n, const double *c1, const double *r1,
 }
 
 const char *sido_version(void) { return "sido-1 (restates sea_ice_drift 0.7.1 pmlib hot path)"; }
+
+/* ------------------------------------------------------------------ feature-tracking matcher */
+
+/* cv2.BFMatcher(NORM_HAMMING).knnMatch(d1, d2, k=2) at the reference's call site ftlib.py:95-96: the two
+ * train descriptors with the smallest Hamming distance, equal distances ordered by train index (pinned
+ * against OpenCV 4.13, tests/test_ftlib.py).  idx/dist: n1 x 2 ints, -1 where there is no such neighbour. */
+int sido_knn_hamming2(const uint8_t *d1, int n1, const uint8_t *d2, int n2, int nbytes, int32_t *idx, int32_t *dist)
+{
+    if (n1 < 0 || n2 < 0 || nbytes <= 0) return SIDO_EINVAL;
+    for (int q = 0; q < n1; ++q) {
+        int b0 = 0x7fffffff, b1 = 0x7fffffff, i0 = -1, i1 = -1;
+        for (int t = 0; t < n2; ++t) {
+            int d = 0;
+            for (int k = 0; k < nbytes; ++k) d += __builtin_popcount((unsigned)(d1[(size_t)q * nbytes + k] ^ d2[(size_t)t * nbytes + k]));
+            if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = t; }
+            else if (d < b1) { b1 = d; i1 = t; }
+        }
+        idx[2 * q] = i0; idx[2 * q + 1] = i1;
+        dist[2 * q] = i0 >= 0 ? b0 : -1; dist[2 * q + 1] = i1 >= 0 ? b1 : -1;
+    }
+    return SIDO_OK;
+}

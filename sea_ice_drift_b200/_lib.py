@@ -23,7 +23,7 @@ SID_HES_NORM, SID_HES_SMTH, SID_MCC_NORM = 1, 2, 4
 EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
     "sid_set_pair", "sid_set_pair_device", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
-    "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian",
+    "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian", "sid_knn_hamming2",
 ]
 
 _lib = None
@@ -73,6 +73,7 @@ def load_library():
                                          C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.sid_match_template.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                            C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
+        lib.sid_knn_hamming2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.sid_get_hessian.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]
         _lib = lib
         return lib
@@ -267,6 +268,18 @@ class Context(object):
                                                  out.ctypes.data))
         self._pair_key = None
         return out
+
+    def knn_hamming2(self, d1, d2):
+        """Two nearest train descriptors per query (Hamming): (idx, dist) int32 arrays of shape (n1, 2)."""
+        d1 = np.ascontiguousarray(d1, dtype=np.uint8)
+        d2 = np.ascontiguousarray(d2, dtype=np.uint8)
+        if d1.ndim != 2 or d2.ndim != 2 or d1.shape[1] != d2.shape[1]:
+            raise ValueError("descriptors must be 2-D uint8 arrays with equal row length")
+        idx = np.full((d1.shape[0], 2), -1, np.int32)
+        dist = np.full((d1.shape[0], 2), -1, np.int32)
+        self._check(self._lib.sid_knn_hamming2(self._h, d1.ctypes.data, d1.shape[0], d2.ctypes.data, d2.shape[0],
+                                               d1.shape[1], idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
 
     def get_hessian(self, ccm, flags=SID_HES_NORM):
         ccm = np.ascontiguousarray(ccm, dtype=np.float32)

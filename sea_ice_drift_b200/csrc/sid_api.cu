@@ -15,6 +15,7 @@
 #include "sid_common.cuh"
 #include "sid_pm_kernel.cuh"
 #include "sid_single_kernels.cuh"
+#include "sid_knn_kernel.cuh"
 
 using namespace sid;
 
@@ -749,6 +750,38 @@ int sid_match_template(sid_ctx *ctx, const uint8_t *img, int H, int W, int64_t p
     rc = match_on_device(ctx, (const uint8_t *)ctx->img2.p, H, W, dp, d_tpl, th, tw, tw, d_isum, d_isq, false, d_ts, d_out);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return SID_OK;
+}
+
+int sid_knn_hamming2(sid_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int desc_bytes,
+                     int32_t *idx, int32_t *dist) {
+    if (!ctx) return SID_EINVAL;
+    if (desc_bytes != 32) return fail(ctx, SID_EUNSUPPORTED, "only 32-byte (ORB) descriptors are implemented");
+    if (n1 < 0 || n2 < 0 || (n1 > 0 && (!d1 || !idx || !dist)) || (n2 > 0 && !d2)) return fail(ctx, SID_EINVAL, "bad knn arguments");
+    if (n1 == 0) return SID_OK;
+    if (n2 == 0) { for (int k = 0; k < 2 * n1; ++k) { idx[k] = -1; dist[k] = -1; } return SID_OK; }
+    CU(cudaSetDevice(ctx->device));
+    const int qblocks = (n1 + KNN_THREADS - 1) / KNN_THREADS;
+    int nseg = (ctx->sm_count * 8 + qblocks - 1) / qblocks;               // >= 8 CTAs per SM in flight
+    nseg = std::max(1, std::min(nseg, std::min(64, (n2 + KNN_TILE - 1) / KNN_TILE)));
+    int seg_len = ((n2 + nseg - 1) / nseg + KNN_TILE - 1) / KNN_TILE * KNN_TILE;
+    nseg = (n2 + seg_len - 1) / seg_len;
+    const size_t b1 = (size_t)n1 * 32, b2 = (size_t)n2 * 32, bp = (size_t)nseg * n1 * sizeof(Top2), bo = (size_t)n1 * 2 * 4;
+    const size_t o2 = (b1 + 255) / 256 * 256, op = o2 + (b2 + 255) / 256 * 256, oi = op + (bp + 255) / 256 * 256, od = oi + (bo + 255) / 256 * 256;
+    int rc = reserve(ctx, ctx->misc, od + bo + 256);
+    if (rc) return rc;
+    unsigned char *base = (unsigned char *)ctx->misc.p;
+    CU(cudaMemcpyAsync(base, d1, b1, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(base + o2, d2, b2, cudaMemcpyHostToDevice, ctx->stream));
+    knn_hamming2_kernel<<<dim3((unsigned)qblocks, (unsigned)nseg), KNN_THREADS, 0, ctx->stream>>>(
+        (const uint4 *)base, n1, (const uint4 *)(base + o2), n2, seg_len, (Top2 *)(base + op));
+    knn_merge_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>((const Top2 *)(base + op), n1, nseg, (int *)(base + oi), (int *)(base + od));
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(idx, base + oi, bo, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(dist, base + od, bo, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     return SID_OK;
