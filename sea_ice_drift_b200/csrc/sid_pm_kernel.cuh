@@ -1,28 +1,29 @@
-// sid_pm_kernel.cuh -- the fused, batched pattern-matching kernel.
+// sid_pm_kernel.cuh -- the fused, batched pattern-matching kernel (and its light tail kernel).
 //
-// One persistent CTA per grid point (work-stealing over an LPT-ordered list) does
-// everything the reference's use_mcc (pmlib.py:176-212) does for that point:
+// One persistent CTA per grid point (work-stealing over a list ordered largest-window-first, next work
+// item prefetched) does everything the reference's use_mcc (pmlib.py:176-212) does for that point:
 //
-//   1. cut the search window of image 2 (pmlib.py:200-202) into shared memory,
-//      re-aligned to 32-bit words with a funnel shift while loading;
-//   2. window sums / sums of squares for every displacement with two sliding-sum
-//      passes (exact integers), folded into sqrt(max(sq - s^2/N, 0)) once per point;
-//   3. for every angle (batches of <= PM_MAX_AB held in shared memory at once):
-//      gather the rotated template from image 1 (get_template, pmlib.py:89-115),
-//      zero-pixel check (pmlib.py:152-154), then the correlation numerators with
-//      exact-integer IDP.4A: each thread owns one output row, one column class
-//      (x mod 4) and TX outputs at stride 4, so every window word it needs is one
-//      SHF of two aligned words and every template word is a warp-wide broadcast;
-//      OpenCV's TM_CCOEFF_NORMED normalisation in FP64 without FMA contraction;
-//      running argmax with np.argmax tie rules; best angle with the reference's
-//      strict '>' rule (pmlib.py:158-165);
-//   4. Hessian at the peak, median (radix select) / std normalisation, optional
-//      mcc_norm (pmlib.py:167-172) and the displacement bookkeeping (pmlib.py:168-169,
-//      209-210).
+//   1. stage the search window of image 2 (pmlib.py:200-202) in shared memory: one TMA 2-D tile load
+//      (cp.async.bulk.tensor + mbarrier; the box must start 16-byte aligned, consumers absorb the 0..15
+//      byte offset), requested during the previous point's tail; fallback for boxes wider than 256 bytes:
+//      warp-per-row aligned loads re-aligned with a funnel shift;
+//   2. window sums / sums of squares for every displacement with two sliding-sum passes (exact
+//      integers), folded into sqrt(max(sq - s^2/N, 0)) once per point;
+//   3. for every angle (batches held in shared memory together): gather the rotated template from
+//      image 1 (get_template, pmlib.py:89-115), zero-pixel check (pmlib.py:152-154), then the exact
+//      integer correlation numerators
+//        - IMMA path (default): mma.sync.m16n8k32 u8 x u8 -> s32, A = raw window rows, B = Toeplitz band
+//          of a template row built on the fly, one warp per 16 x 24 output tile and all resident angles;
+//        - dp4a path: IDP.4A, one thread per output row / column class / TX outputs at stride 4;
+//      OpenCV's TM_CCOEFF_NORMED normalisation in FP64 without FMA contraction; running argmax with
+//      np.argmax tie rules; best angle with the reference's strict '>' rule (pmlib.py:158-165);
+//   4. Hessian at the peak, median (radix select) / std normalisation, optional mcc_norm
+//      (pmlib.py:167-172) and the displacement bookkeeping (pmlib.py:168-169, 209-210) -- inside this
+//      kernel, or, for small result maps, in pm_tail_kernel at much higher occupancy (split tail).
 //
-// Result-sized arrays (window statistics, NCC maps) live in a per-CTA global scratch
-// slab that stays L2-resident; only O(R^2) traffic per angle goes there, against
-// O(R^2 s^2) integer MACs out of shared memory / registers.
+// Result-sized arrays (window statistics, NCC maps) live in shared memory when window + templates +
+// scratch fit in a third of an SM, else in a per-CTA global slab that stays L2-resident; either way only
+// O(R^2) traffic per angle goes there, against O(R^2 s^2) integer MACs out of shared memory / registers.
 #pragma once
 #include <cuda.h>
 #include "sid_common.cuh"
@@ -30,7 +31,7 @@
 namespace sid {
 
 constexpr int PM_THREADS = 256;
-constexpr int PM_MAX_AB = 4;      // angles whose templates sit in shared memory together
+constexpr int PM_MAX_AB = 4;      // angles whose templates sit in shared memory together (dp4a path; IMMA: PM_IMMA_AB)
 constexpr int PM_SEG = 16;        // outputs per horizontal sliding-sum work item
 constexpr int PM_VSEG = 8;        // outputs per vertical sliding-sum work item
 constexpr int PM_WIN_SLACK = 64;  // words readable past the staged window
