@@ -67,3 +67,127 @@ def use_mcc_batch_sharded(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alph
         import torch
         device = torch.device('cuda', torch.cuda.current_device())
     return gather_rows(local, idx, n, dist, device)
+
+
+def shard_pairs(n_pairs, world_size, rank):
+    """Indices of the image pairs of a time series that rank ``rank`` processes (BASELINE configs[4]: whole
+    pairs are dealt round-robin, so no image is replicated and nothing is exchanged during the compute)."""
+    return list(range(rank, n_pairs, world_size))
+
+
+def use_mcc_series(pairs, img_size, alpha0=0.0, n_contexts=1, compute=None, gather=True, **kwargs):
+    """Pattern matching for a time series of image pairs: the batched form of calling the reference's
+    ``pattern_matching`` Pool section (pmlib.py:430-448) once per pair.
+
+    ``pairs`` is a sequence whose items are ``(img1, img2, c1, r1, c2fg, r2fg, border)`` tuples or zero-argument
+    callables returning one (lazy loading: a rank only ever touches its own pairs).  Pairs are dealt round-robin
+    to the ranks of the process group (``shard_pairs``); inside a rank every pair goes through
+    ``Context.run_pair`` (banded upload overlapped with the kernels).  ``n_contexts`` > 1 lets several contexts work
+    through the rank's pairs concurrently (threads); measured on B200 this is SLOWER than one context (13.2 vs
+    14.0 / 16.8 ms per EW pair for 1 / 2 / 3 contexts: the persistent kernels and band uploads of two pairs only
+    delay each other), so the default is 1.  Returns the list of (n_k, 5) tables ``[c2, r2, angle, r, h]`` in pair order -- complete on
+    every rank when ``gather`` is true (one all-gather of the padded tables); with ``gather='root'`` only rank 0
+    reads the gathered tables back (the other ranks keep ``None`` for foreign pairs, as with ``gather=False``) --
+    the cheaper choice when one process writes the products, since the read-back is host-memory bound.
+
+    ``compute(ctx_slot, img1, img2, c1, r1, c2fg, r2fg, border)`` is the per-pair function (the GPU
+    ``Context.run_pair`` by default; the CPU tests inject a stand-in)."""
+    import queue
+    import threading
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    mine = shard_pairs(len(pairs), world, rank)
+    results = [None] * len(pairs)
+    n_contexts = max(1, min(int(n_contexts), max(1, len(mine))))
+    if compute is None:
+        from . import _lib
+        flags = _lib.flags_from_kwargs(kwargs)
+        angles = kwargs.get('angles', [-3, 0, 3])
+        rot_order = kwargs.get('rot_order', 0)
+        ctxs = [_lib.default_context()] + [_lib.Context(_lib.default_context().device) for _ in range(n_contexts - 1)]
+
+        def compute(slot, img1, img2, c1, r1, c2fg, r2fg, border):
+            return ctxs[slot].run_pair(img1, img2, c1, r1, c2fg, r2fg, border, img_size, angles, alpha0,
+                                       rot_order=rot_order, flags=flags)
+    work = queue.Queue()
+    for k in mine:
+        work.put(k)
+    errors = []
+
+    def worker(slot):
+        while True:
+            try:
+                k = work.get_nowait()
+            except queue.Empty:
+                return
+            try:
+                item = pairs[k]() if callable(pairs[k]) else pairs[k]
+                results[k] = np.asarray(compute(slot, *item), dtype=np.float64).reshape(-1, 5)
+            except BaseException as exc:      # surfaced on the calling thread
+                errors.append(exc)
+                return
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(1, n_contexts)]
+    for t in threads:
+        t.start()
+    worker(0)
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    if dist is None or not gather:
+        return results
+    return _gather_series(results, mine, len(pairs), dist, root_only=(gather == 'root'))
+
+
+_pinned = {}
+
+
+def _staging(name, shape, device):
+    """Cached page-locked float64 staging buffer (NCCL path only; plain tensors on CPU/gloo)."""
+    import torch
+    if device.type != 'cuda':
+        return torch.empty(shape, dtype=torch.float64)
+    n = int(np.prod(shape))
+    buf = _pinned.get(name)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty((max(n, 1),), dtype=torch.float64).pin_memory()
+        _pinned[name] = buf
+    return buf[:n].view(*shape)
+
+
+def _gather_series(results, mine, n_pairs, dist, root_only=False):
+    """Exchange the per-pair tables: one all-gather of the table lengths, one of the NaN-padded tables.  On
+    NCCL the tables travel host -> device -> all ranks -> host through cached pinned staging buffers."""
+    import torch
+    world = dist.get_world_size()
+    device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    per_rank = -(-n_pairs // world)
+    sizes = torch.full((per_rank,), -1, dtype=torch.int64)
+    for j, k in enumerate(mine):
+        sizes[j] = results[k].shape[0]
+    all_sizes = torch.empty((world * per_rank,), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_sizes, sizes.to(device))
+    all_sizes = all_sizes.cpu().numpy().reshape(world, per_rank)
+    n_max = max(1, int(all_sizes.max()))
+    pack = _staging('send', (per_rank, n_max, 5), device)
+    for j in range(per_rank):
+        n_j = results[mine[j]].shape[0] if j < len(mine) else 0
+        if n_j:
+            pack[j, :n_j] = torch.from_numpy(results[mine[j]])
+        pack[j, n_j:] = float('nan')
+    gathered = torch.empty((world * per_rank, n_max, 5), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(gathered, pack.to(device, non_blocking=True))
+    if root_only and dist.get_rank() != 0:
+        return results                      # the exchange on the device is collective; only rank 0 reads it back
+    host = _staging('recv', (world, per_rank, n_max, 5), device)
+    host.copy_(gathered.view(world, per_rank, n_max, 5), non_blocking=True)
+    if device.type == 'cuda':
+        torch.cuda.current_stream().synchronize()
+    g = host.numpy()
+    out = [None] * n_pairs
+    for r in range(world):
+        for j, k in enumerate(shard_pairs(n_pairs, world, r)):
+            # own tables are returned as they are; foreign ones are copied out of the reusable staging buffer
+            out[k] = results[k] if results[k] is not None else g[r, j, :int(all_sizes[r, j])].copy()
+    return out

@@ -255,7 +255,7 @@ def test_sharded_pattern_matching_over_nccl_two_gpus():
            "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tests", "multi_gpu_sharded.py")]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:]
-    assert "== single GPU: True" in res.stdout
+    assert "ranks) == single GPU: True" in res.stdout and "series(2 ranks) == single GPU: True" in res.stdout
 
 
 def test_time_series_of_pairs_through_one_context(gpu_ctx):
@@ -266,6 +266,24 @@ def test_time_series_of_pairs_through_one_context(gpu_ctx):
         got = gpu_ctx.run_pair(img1, img2, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
         ref, _ = co.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=cfg["angles"])
         assert_equals_exact_oracle(got, ref)
+
+
+def test_series_driver_two_contexts_equal_exact_oracle():
+    """sharding.use_mcc_series on one GPU: pairs of different shapes and grid sizes worked through by two
+    contexts concurrently (threads), one of them loaded lazily -- every table equals the exact oracle."""
+    from sea_ice_drift_b200.sharding import use_mcc_series
+    items = []
+    for k in range(5):
+        img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=30 + k, side=600 + 48 * k, grid=10 + 3 * k)
+        items.append((img1, img2, c1, r1, c2, r2, b))
+    pairs = list(items)
+    pairs[3] = lambda: items[3]
+    for n_contexts in (1, 2):
+        tables = use_mcc_series(pairs, 35, 0.0, n_contexts=n_contexts, angles=[-3, 0, 3])
+        assert len(tables) == 5
+        for (img1, img2, c1, r1, c2, r2, b), got in zip(items, tables):
+            ref, _ = co.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=[-3, 0, 3])
+            assert_equals_exact_oracle(got, ref)
 
 
 @pytest.mark.parametrize("seed", range(10))

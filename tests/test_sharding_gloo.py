@@ -68,3 +68,89 @@ def test_two_rank_gather_equals_single_process():
     for rank, table, calls in got:
         assert np.array_equal(table, single, equal_nan=True)
         assert len(calls) == 1 and abs(calls[0] - len(c1) / 2) <= 1
+
+
+def _series_pairs():
+    """Five small pairs with different grid sizes (ragged tables), the last one lazily loaded."""
+    from sea_ice_drift_b200 import synthetic as syn
+    items = []
+    for k in range(5):
+        img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=20 + k, side=500 + 32 * k, grid=5 + k)
+        items.append((img1, img2, c1, r1, c2, r2, b))
+    last = items[-1]
+    items[-1] = lambda: last
+    return items
+
+
+def _series_compute(slot, img1, img2, c1, r1, c2, r2, b):
+    from tests.test_host_api import oracle_compute
+    return oracle_compute(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=[-3, 0, 3])
+
+
+def _series_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from sea_ice_drift_b200.sharding import use_mcc_series
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        seen = []
+
+        def compute(slot, *a):
+            seen.append((slot, len(a[2])))
+            return _series_compute(slot, *a)
+        tables = use_mcc_series(_series_pairs(), 35, 0.0, n_contexts=2, compute=compute)
+        rooted = use_mcc_series(_series_pairs(), 35, 0.0, compute=_series_compute, gather='root')
+        assert all(t is not None for t in rooted) if rank == 0 else [t is None for t in rooted] == [True, False] * 2 + [True]
+        if rank == 0:
+            assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(rooted, tables))
+        q.put((rank, tables, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_pairs_partition():
+    from sea_ice_drift_b200.sharding import shard_pairs
+    for world in (1, 2, 3, 8):
+        parts = [shard_pairs(16, world, r) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(16))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert shard_pairs(3, 8, 5) == []
+
+
+def test_series_single_process_and_error_propagation():
+    from sea_ice_drift_b200.sharding import use_mcc_series
+    pairs = _series_pairs()
+    tables = use_mcc_series(pairs, 35, 0.0, n_contexts=3, compute=_series_compute)
+    for item, t in zip(pairs, tables):
+        item = item() if callable(item) else item
+        assert np.array_equal(t, _series_compute(0, *item), equal_nan=True)
+    assert use_mcc_series([], 35, compute=_series_compute) == []
+
+    def boom(slot, *a):
+        raise RuntimeError("pair failed")
+    with pytest.raises(RuntimeError, match="pair failed"):
+        use_mcc_series(pairs, 35, compute=boom)
+
+
+def test_two_rank_series_gather_equals_single_process():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_series_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pairs = _series_pairs()
+    want = [_series_compute(0, *(it() if callable(it) else it)) for it in pairs]
+    for rank, tables, seen in got:
+        assert len(tables) == len(want)
+        for t, w in zip(tables, want):
+            assert np.array_equal(t, w, equal_nan=True)
+        assert len(seen) == (3 if rank == 0 else 2)          # pairs 0,2,4 / 1,3 -- nothing computed twice
