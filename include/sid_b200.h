@@ -166,6 +166,16 @@ int sid_match_template(sid_ctx *ctx,
 int sid_knn_hamming2(sid_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int desc_bytes,
                      int32_t *idx, int32_t *dist);
 
+/* Deformation of triangular elements (the consumer side of the hot path): what
+ * get_deformation_on_triangulation (libdefor.py:50-99) and get_deformation_elems (libdefor.py:4-48) return.
+ * Host pointers.  x, y, u, v: n node values; tri: m x 3 node indices, row-major; area_in: optional m element
+ * areas (NULL = Heron's formula from the side lengths, as get_deformation_on_triangulation does).
+ * Outputs, m doubles each: e1 divergence, e2 shear, e3 vorticity, area, perimeter; NaN for an element with a
+ * node index outside [0, n). */
+int sid_deformation(sid_ctx *ctx, int n, const double *x, const double *y, const double *u, const double *v,
+                    int m, const int32_t *tri, const double *area_in,
+                    double *e1, double *e2, double *e3, double *area, double *perim);
+
 /* get_hessian of a float32 map (rows x cols) -> float32 map of the same shape. */
 int sid_get_hessian(sid_ctx *ctx, const float *ccm, int rows, int cols,
                     unsigned flags, float *out);

@@ -7,6 +7,7 @@ from .pmlib import (get_hessian, get_template, match_template, rotate_and_match,
 from .lib import interpolation_poly, interpolation_near
 from .seaicedrift import SeaIceDrift
 from . import ftlib
+from . import libdefor
 
 __version__ = "0.1.0"
 __all__ = ['get_hessian', 'get_template', 'match_template', 'rotate_and_match', 'use_mcc', 'use_mcc_mp',

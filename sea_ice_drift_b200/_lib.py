@@ -24,6 +24,7 @@ EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
     "sid_set_pair", "sid_set_pair_device", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
     "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian", "sid_knn_hamming2",
+    "sid_deformation",
 ]
 
 _lib = None
@@ -75,6 +76,7 @@ def load_library():
                                            C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
         lib.sid_knn_hamming2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.sid_get_hessian.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+        lib.sid_deformation.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7
         _lib = lib
         return lib
 
@@ -280,6 +282,27 @@ class Context(object):
         self._check(self._lib.sid_knn_hamming2(self._h, d1.ctypes.data, d1.shape[0], d2.ctypes.data, d2.shape[0],
                                                d1.shape[1], idx.ctypes.data, dist.ctypes.data))
         return idx, dist
+
+    def deformation(self, x, y, u, v, tri, area=None):
+        """(e1, e2, e3, area, perimeter) of the m elements ``tri`` (m x 3 node indices) from node values."""
+        x, y, u, v = [np.ascontiguousarray(np.ravel(k), dtype=np.float64) for k in (x, y, u, v)]
+        n = x.size
+        if any(k.size != n for k in (y, u, v)):
+            raise ValueError("node arrays must have equal length")
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        if tri.ndim != 2 or tri.shape[1] != 3:
+            raise ValueError("triangulation must be an (m, 3) index array")
+        m = tri.shape[0]
+        ain = None
+        if area is not None:
+            ain = np.ascontiguousarray(np.ravel(area), dtype=np.float64)
+            if ain.size != m:
+                raise ValueError("one area per element expected")
+        outs = [np.full(m, np.nan) for _ in range(5)]
+        self._check(self._lib.sid_deformation(self._h, n, x.ctypes.data, y.ctypes.data, u.ctypes.data, v.ctypes.data,
+                                              m, tri.ctypes.data, ain.ctypes.data if ain is not None else None,
+                                              *[o.ctypes.data for o in outs]))
+        return tuple(outs)
 
     def get_hessian(self, ccm, flags=SID_HES_NORM):
         ccm = np.ascontiguousarray(ccm, dtype=np.float32)

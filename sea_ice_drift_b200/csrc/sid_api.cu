@@ -16,6 +16,7 @@
 #include "sid_pm_kernel.cuh"
 #include "sid_single_kernels.cuh"
 #include "sid_knn_kernel.cuh"
+#include "sid_defor_kernel.cuh"
 
 using namespace sid;
 
@@ -782,6 +783,51 @@ int sid_knn_hamming2(sid_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2,
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(idx, base + oi, bo, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(dist, base + od, bo, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return SID_OK;
+}
+
+int sid_deformation(sid_ctx *ctx, int n, const double *x, const double *y, const double *u, const double *v,
+                    int m, const int32_t *tri, const double *area_in,
+                    double *e1, double *e2, double *e3, double *area, double *perim) {
+    if (!ctx) return SID_EINVAL;
+    if (n < 0 || m < 0 || (n > 0 && (!x || !y || !u || !v)) || (m > 0 && (!tri || !e1 || !e2 || !e3 || !area || !perim)))
+        return fail(ctx, SID_EINVAL, "bad deformation arguments");
+    if (m == 0) return SID_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bn = ((size_t)n * 8 + 255) / 256 * 256, bm = ((size_t)m * 8 + 255) / 256 * 256;
+    const size_t bt = ((size_t)m * 12 + 255) / 256 * 256;
+    int rc = reserve(ctx, ctx->misc, 4 * bn + bt + 6 * bm + 256);
+    if (rc) return rc;
+    unsigned char *base = (unsigned char *)ctx->misc.p;
+    DeforArgs a;
+    const double *src[4] = {x, y, u, v};
+    double *dn[4];
+    for (int k = 0; k < 4; ++k) {
+        dn[k] = (double *)(base + k * bn);
+        if (n > 0) CU(cudaMemcpyAsync(dn[k], src[k], (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    a.x = dn[0]; a.y = dn[1]; a.u = dn[2]; a.v = dn[3];
+    int32_t *dt = (int32_t *)(base + 4 * bn);
+    CU(cudaMemcpyAsync(dt, tri, (size_t)m * 12, cudaMemcpyHostToDevice, ctx->stream));
+    a.tri = dt;
+    double *dm = (double *)(base + 4 * bn + bt);
+    a.e1 = dm; a.e2 = (double *)((char *)dm + bm); a.e3 = (double *)((char *)dm + 2 * bm);
+    a.area = (double *)((char *)dm + 3 * bm); a.perim = (double *)((char *)dm + 4 * bm);
+    double *dain = (double *)((char *)dm + 5 * bm);
+    a.area_in = nullptr;
+    if (area_in) {
+        CU(cudaMemcpyAsync(dain, area_in, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        a.area_in = dain;
+    }
+    a.n = n; a.m = m;
+    deformation_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    double *dst[5] = {e1, e2, e3, area, perim};
+    for (int k = 0; k < 5; ++k)
+        CU(cudaMemcpyAsync(dst[k], (char *)dm + k * bm, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     return SID_OK;
