@@ -40,8 +40,9 @@ def test_product_arm_json_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 2 * 1500 * 1500 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert 0 < d["e2e"]["value"] <= d["value"] * 1.05
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
-        assert key in d["roofline"] and key in d["roofline_tensor"]
-    assert d["roofline_tensor"]["bound"] == "tensor"
+        assert key in d["roofline"] and key in d["roofline_fma"]
+    assert d["roofline"]["bound"] in ("hbm", "tensor") and d["roofline_fma"]["bound"] == "fma"
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     p = d["parity"]
     assert p["nan_pattern_equal"] and p["position_angle_equal"] == p["compared"] == p["r_bit_equal"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
