@@ -202,6 +202,9 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # one process per GPU: keep this rank (and the pinned buffers it allocates from here on) on the GPU's NUMA node
+    from sea_ice_drift_b200.sharding import bind_rank_to_gpu
+    bound = None if os.environ.get("SID_NO_BIND") else bind_rank_to_gpu(local_rank)
     img1p = torch.from_numpy(img1).pin_memory().numpy()
     img2p = torch.from_numpy(img2).pin_memory().numpy()
 
@@ -333,7 +336,9 @@ def main_ours(args):
                 "config": {"workload": workload_description(args.workload, cfg, n), "points_per_gpu": n,
                            "l2": "inputs larger than L2: 2 x %.0f MB image pair per GPU, no flush between steps"
                                  % (img1.nbytes / 1e6),
-                           "parallelism": "grid points sharded per GPU, one pair per rank, no data-path collective"},
+                           "parallelism": "grid points sharded per GPU, one pair per rank, no data-path collective",
+                           "host_binding": ("rank bound to the %d cores local to its GPU (NVML affinity)" % len(bound)) if bound
+                                           else "none"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": 1e3 * dt_e2e / e2e_steps,

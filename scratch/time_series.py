@@ -40,6 +40,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from sea_ice_drift_b200.sharding import bind_rank_to_gpu
+    bound = None if os.environ.get("SID_NO_BIND") else bind_rank_to_gpu(local)
     distinct = []
     for k in range(args.distinct):
         img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg5", seed=k, side=args.side or None, grid=args.grid or None)
@@ -110,7 +112,7 @@ def main():
                           "contexts_per_gpu": args.contexts, "gather": args.gather, "seconds": round(secs, 5),
                           "vectors_per_s": round(n_total / secs, 1), "ms_per_pair": round(1e3 * secs / args.pairs, 3),
                           "all_times_s": [round(x, 5) for x in times],
-                          "compute_and_copies_s": round(float(bd[0]), 5), "gather_s": round(float(bd[1]), 5), "host_images": "pinned",
+                          "compute_and_copies_s": round(float(bd[0]), 5), "gather_s": round(float(bd[1]), 5), "host_images": "pinned", "cores_bound": len(bound) if bound else 0,
                           "includes": "image H2D, point H2D, result D2H, all-gather of tables",
                           "parity_checked": checked, "parity_unexplained": bad,
                           "parity_max_dr": max_dr, "parity_max_dh_rel": max_dh}))

@@ -191,3 +191,30 @@ def _gather_series(results, mine, n_pairs, dist, root_only=False):
             # own tables are returned as they are; foreign ones are copied out of the reusable staging buffer
             out[k] = results[k] if results[k] is not None else g[r, j, :int(all_sizes[r, j])].copy()
     return out
+
+
+def bind_rank_to_gpu(device):
+    """Restrict the calling process to the CPU cores that are local to CUDA device ``device`` (NVML's CPU
+    affinity of the GPU), so that page-locked host buffers allocated afterwards -- the image pairs that
+    ``run_pair`` uploads every step -- live on the GPU's own NUMA node.  For one-process-per-GPU jobs; call it
+    before allocating pinned memory.  Returns the sorted core list, or None when NVML / the affinity API is not
+    available or the result would be empty (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + bit for w, mask in enumerate(words) for bit in range(64) if (int(mask) >> bit) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:       # no NVML, no permission, unknown device: leave the affinity alone
+        return None
