@@ -100,8 +100,10 @@ int sid_run(sid_ctx *ctx, int64_t n,
 /* sid_set_pair + sid_run in ONE call, with the host-to-device copy of the image pair overlapped
  * with the computation: the pair is uploaded in row bands on a second stream and the points are
  * processed band by band as soon as every image row they touch has arrived.  Results are
- * identical to sid_set_pair followed by sid_run; the pair stays resident afterwards.  Use pinned
- * (page-locked) host images for the overlap to take effect. */
+ * identical to sid_set_pair followed by sid_run; the pair stays resident afterwards.  Page-locked host
+ * images are copied by DMA directly; pageable ones (plain malloc / NumPy memory) go band by band through
+ * a pinned double buffer that a few host threads fill while the previous band is in flight (EW-sized
+ * pair, B200: 6.1 ms per call pinned, 9.7 ms pageable, against 26 ms for a plain pageable cudaMemcpy). */
 int sid_run_pair(sid_ctx *ctx,
                  const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
                  const uint8_t *img2, int rows2, int cols2, int64_t pitch2,

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sid_b200.h"
@@ -55,6 +56,10 @@ struct sid_ctx {
     cudaEvent_t k_ev[2] = {};                // bracket the last fused-kernel launch (sid_last_kernel_ms)
     bool k_ev_valid = false;
     long long tail_hint_n = 0;               // total points of the current host call (sizes the tail hand-off once)
+    // staged upload of pageable host images (sid_run_pair): pinned double buffer + "slot free again" events
+    void *stage = nullptr;
+    size_t stage_cap = 0;
+    cudaEvent_t stage_event[2] = {};
     void *encode_tiled = nullptr;            // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
     bool encode_tried = false;
 };
@@ -370,6 +375,8 @@ void sid_destroy(sid_ctx *ctx) {
                       &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    for (cudaEvent_t e : ctx->stage_event) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->k_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->slot_event) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : ctx->band_stream) if (st) cudaStreamDestroy(st);
@@ -447,6 +454,32 @@ static int upload_angles(sid_ctx *ctx, int n_angles, const double *angles, const
 }
 
 namespace {
+
+// true when `p` is ordinary pageable host memory (cudaMemcpyAsync from it is a slow, synchronous staged copy)
+bool is_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// rows x width bytes from (src, spitch) to (dst, dpitch), split over `nthreads` host threads
+void copy_rows_parallel(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, int rows, int nthreads) {
+    if (rows <= 0) return;
+    auto work = [=](int r0, int r1) {
+        if (spitch == width && dpitch == width) { memcpy(dst + (size_t)r0 * width, src + (size_t)r0 * width, (size_t)(r1 - r0) * width); return; }
+        for (int r = r0; r < r1; ++r) memcpy(dst + (size_t)r * dpitch, src + (size_t)r * spitch, width);
+    };
+    nthreads = std::max(1, std::min(nthreads, rows));
+    if (nthreads == 1) { work(0, rows); return; }
+    std::vector<std::thread> pool;
+    const int per = (rows + nthreads - 1) / nthreads;
+    for (int t = 1; t < nthreads; ++t) {
+        const int r0 = t * per, r1 = std::min(rows, r0 + per);
+        if (r0 < r1) pool.emplace_back(work, r0, r1);
+    }
+    work(0, std::min(rows, per));
+    for (std::thread &t : pool) t.join();
+}
 
 struct HostPair {
     const uint8_t *img1, *img2;
@@ -562,22 +595,53 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->band_event[MAX_BANDS], 0));
         if (fresh1) CU(cudaMemsetAsync(ctx->img1.p, 0, ctx->img1.cap, ctx->copy_stream));
         if (fresh2) CU(cudaMemsetAsync(ctx->img2.p, 0, ctx->img2.cap, ctx->copy_stream));
-        for (int k = 0; k < nbands; ++k) {
-            const int ya = k * band_rows;
-            const int n1 = std::min(band_rows, pair->rows1 - ya), n2 = std::min(band_rows, pair->rows2 - ya);
-            if (n1 > 0)
-                CU(cudaMemcpy2DAsync((char *)ctx->img1.p + (size_t)ya * ctx->pitch1, (size_t)ctx->pitch1,
-                                     pair->img1 + (size_t)ya * pair->pitch1, (size_t)pair->pitch1, (size_t)pair->cols1,
-                                     (size_t)n1, cudaMemcpyHostToDevice, ctx->copy_stream));
-            if (n2 > 0)
-                CU(cudaMemcpy2DAsync((char *)ctx->img2.p + (size_t)ya * ctx->pitch2, (size_t)ctx->pitch2,
-                                     pair->img2 + (size_t)ya * pair->pitch2, (size_t)pair->pitch2, (size_t)pair->cols2,
-                                     (size_t)n2, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CU(cudaEventRecord(ctx->band_event[k], ctx->copy_stream));
-        }
         ctx->rows1 = pair->rows1; ctx->cols1 = pair->cols1; ctx->rows2 = pair->rows2; ctx->cols2 = pair->cols2;
     }
 
+    // Pageable host images (plain NumPy arrays): each band goes through a pinned double buffer, filled by a few host
+    // threads while the previous band's DMA and kernels run; band k's kernels are launched right behind its copy.
+    bool staged = false;
+    int copy_threads = 1;
+    if (pair) {
+        staged = is_pageable(pair->img1) || is_pageable(pair->img2);
+        if (const char *e = getenv("SID_STAGED_UPLOAD")) staged = e[0] != '0';
+        copy_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+        if (const char *e = getenv("SID_UPLOAD_THREADS")) copy_threads = std::max(1, std::min(64, atoi(e)));
+    }
+    const size_t slot_bytes = pair ? ((size_t)band_rows * ((size_t)pair->cols1 + (size_t)pair->cols2) + 255) / 256 * 256 : 0;
+    if (staged) {
+        if (2 * slot_bytes > ctx->stage_cap) {
+            if (ctx->stage) { cudaFreeHost(ctx->stage); ctx->stage = nullptr; ctx->stage_cap = 0; }
+            if (cudaMallocHost(&ctx->stage, 2 * slot_bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SID_ENOMEM, "pinned staging allocation failed"); }
+            ctx->stage_cap = 2 * slot_bytes;
+        }
+        for (int k = 0; k < 2; ++k) if (!ctx->stage_event[k]) CU(cudaEventCreateWithFlags(&ctx->stage_event[k], cudaEventDisableTiming));
+    }
+    auto enqueue_band_copy = [&](int k) -> int {
+        const int ya = k * band_rows;
+        const int n1 = std::min(band_rows, pair->rows1 - ya), n2 = std::min(band_rows, pair->rows2 - ya);
+        const uint8_t *s1 = pair->img1 + (size_t)ya * pair->pitch1, *s2 = pair->img2 + (size_t)ya * pair->pitch2;
+        size_t sp1 = (size_t)pair->pitch1, sp2 = (size_t)pair->pitch2;
+        if (staged) {
+            const int slot = k & 1;
+            if (k >= 2) CU(cudaEventSynchronize(ctx->stage_event[slot]));      // the DMA of band k-2 has drained this slot
+            uint8_t *d1 = (uint8_t *)ctx->stage + (size_t)slot * slot_bytes, *d2 = d1 + (size_t)band_rows * pair->cols1;
+            if (n1 > 0) copy_rows_parallel(d1, (size_t)pair->cols1, s1, sp1, (size_t)pair->cols1, n1, copy_threads);
+            if (n2 > 0) copy_rows_parallel(d2, (size_t)pair->cols2, s2, sp2, (size_t)pair->cols2, n2, copy_threads);
+            s1 = d1; s2 = d2; sp1 = (size_t)pair->cols1; sp2 = (size_t)pair->cols2;
+        }
+        if (n1 > 0)
+            CU(cudaMemcpy2DAsync((char *)ctx->img1.p + (size_t)ya * ctx->pitch1, (size_t)ctx->pitch1, s1, sp1, (size_t)pair->cols1,
+                                 (size_t)n1, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (n2 > 0)
+            CU(cudaMemcpy2DAsync((char *)ctx->img2.p + (size_t)ya * ctx->pitch2, (size_t)ctx->pitch2, s2, sp2, (size_t)pair->cols2,
+                                 (size_t)n2, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (staged) CU(cudaEventRecord(ctx->stage_event[k & 1], ctx->copy_stream));
+        CU(cudaEventRecord(ctx->band_event[k], ctx->copy_stream));
+        return SID_OK;
+    };
+    if (pair && !staged)
+        for (int k = 0; k < nbands; ++k) if ((rc = enqueue_band_copy(k))) return rc;
 
     const double *dp = (const double *)ctx->pts.p;
     ctx->tail_hint_n = n;
@@ -591,6 +655,7 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
         for (int k = 0; k < 2; ++k) CU(cudaStreamWaitEvent(ctx->band_stream[k], ctx->slot_event[0], 0));
     }
     for (int k = 0; k < nbands; ++k) {
+        if (staged && (rc = enqueue_band_copy(k))) return rc;
         // consecutive bands go to alternating streams: the next band's CTAs fill the SMs while this one drains
         cudaStream_t st = two_streams ? ctx->band_stream[k & 1] : ctx->stream;
         if (pair) CU(cudaStreamWaitEvent(st, ctx->band_event[k], 0));
