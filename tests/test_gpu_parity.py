@@ -3,6 +3,7 @@ vectors of the live reference, (b) the exact CPU oracle on seeded inputs, and (c
 size-independent properties at BASELINE.json's full sizes.  Needs a B200 (-m gpu)."""
 import contextlib
 import io
+import os
 
 import numpy as np
 import pytest
@@ -240,6 +241,33 @@ def test_run_pair_overlapped_upload_equals_set_pair_then_run(gpu_ctx):
     assert np.array_equal(got2, ref, equal_nan=True)
     empty = gpu_ctx.run_pair(img1, img2, [], [], [], [], [], 35, cfg["angles"], 0.0)
     assert empty.shape == (0, 5)
+
+
+def test_run_pair_images_of_different_shapes_pinned_and_pageable(gpu_ctx):
+    """Image 2 larger than image 1, image 1 cut short (its bottom grid points lose their template -> NaN rows), several
+    upload bands with unequal row counts per image: the pageable path (NumPy memory, staged through the pinned
+    double buffer by host threads) and the pinned path (direct DMA) both equal the exact oracle."""
+    import torch
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=9, side=2300, grid=40)
+    img2b = np.zeros((2600, 2450), np.uint8)
+    img2b[:2300, :2300] = img2
+    img1s = np.ascontiguousarray(img1[:2100])
+    ref, _ = co.use_mcc_batch(c1, r1, c2, r2, b, img1s, img2b, 35, 0.0, angles=cfg["angles"])
+    assert np.isnan(ref[:, 0]).any() and not np.isnan(ref[:, 0]).all()
+    got_pageable = gpu_ctx.run_pair(img1s, img2b, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
+    assert_equals_exact_oracle(got_pageable, ref)
+    p1 = torch.from_numpy(img1s).pin_memory().numpy()
+    p2 = torch.from_numpy(img2b).pin_memory().numpy()
+    got_pinned = gpu_ctx.run_pair(p1, p2, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
+    assert np.array_equal(got_pinned, got_pageable, equal_nan=True)
+    for forced in ("1", "0"):                      # either upload path on either kind of memory
+        os.environ["SID_STAGED_UPLOAD"] = forced
+        try:
+            a = gpu_ctx.run_pair(p1, p2, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
+            bb = gpu_ctx.run_pair(img1s, img2b, c1, r1, c2, r2, b, 35, cfg["angles"], 0.0)
+        finally:
+            del os.environ["SID_STAGED_UPLOAD"]
+        assert np.array_equal(a, got_pageable, equal_nan=True) and np.array_equal(bb, got_pageable, equal_nan=True)
 
 
 def test_sharded_pattern_matching_over_nccl_two_gpus():
