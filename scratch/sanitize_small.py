@@ -9,3 +9,17 @@ out = ctx.run_pair(img1, img2, c1, r1, c2, r2, b, 35, [-3, 0, 3], 0.0)
 out2 = ctx.run(c1, r1, c2, r2, b, 35, list(range(-3, 4)), 0.0, rot_order=1, flags=7)
 out3 = ctx.run(c1[:20], r1[:20], c2[:20], r2[:20], b[:20] + 40, 50, [0, 2], 0.0)
 print("ok", np.isnan(out[:, 0]).sum(), np.isnan(out2[:, 0]).sum(), np.isnan(out3[:, 0]).sum())
+# multi-band pageable upload (staged through the pinned double buffer), matcher, deformation, single-call entry points
+img1b, img2b, d1, e1, d2, e2, bb, _ = syn.make_config("cfg2", seed=2, side=1300, grid=6)
+out4 = ctx.run_pair(img1b[:1100], img2b, d1, e1, d2, e2, bb, 35, [-3, 0, 3], 0.0)
+rng = np.random.default_rng(1)
+q = rng.integers(0, 256, (700, 32), dtype=np.uint8); t = rng.integers(0, 256, (900, 32), dtype=np.uint8)
+idx, dist = ctx.knn_hamming2(q, t)
+x = rng.uniform(0, 1e5, 500); y = rng.uniform(0, 1e5, 500)
+from sea_ice_drift_b200 import libdefor
+tri = libdefor.triangulate(x, y)
+e = ctx.deformation(x, y, rng.normal(0, .1, 500), rng.normal(0, .1, 500), tri)
+tpl = ctx.get_template(img1, 300.5, 310.25, 2.0, 35)
+res = ctx.match_template(img2[200:300, 220:330], tpl)
+hes = ctx.get_hessian(res)
+print("ok2", np.isnan(out4[:, 0]).sum(), idx.shape, len(tri), tpl.shape, res.shape, float(hes.max()))
