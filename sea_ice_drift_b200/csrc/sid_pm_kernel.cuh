@@ -301,7 +301,8 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
             arow8 += wpw;
             trow += tpw;
         }
-        // epilogue: C fragment (row g / g+8, columns 2*tig, 2*tig+1 of each 8-column block)
+        // ---- epilogue, two steps.  (1) The raw correlation sums go to their map slots as integers: C fragment =
+        //      rows g / g+8, columns 2*tig, 2*tig+1 of each 8-column block.
 #pragma unroll
         for (int b = 0; b < 3; ++b)
 #pragma unroll
@@ -311,22 +312,51 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
                     const int y = y0 + g + 8 * h, x = x0 + 8 * b + 2 * tig + e - ab;
                     if (y < RH && x >= 0 && x < RW) {
                         const int idx = y * RW + x;
-                        const uint32_t ws = wsum[idx];
-                        const double wd = wden[idx];
-                        const int q = 2 * h + e;
-                        const Ncc3 r3 = ncc_value_call3(acc[0][b][q], acc[NBA > 1 ? 1 : 0][b][q], acc[NBA > 2 ? 2 : 0][b][q], ws, wd,
-                                                        S.st[0].mean, S.st[0].norm, S.st[NBA > 1 ? 1 : 0].mean, S.st[NBA > 1 ? 1 : 0].norm,
-                                                        S.st[NBA > 2 ? 2 : 0].mean, S.st[NBA > 2 ? 2 : 0].norm);
-                        const float vv[3] = {r3.v0, r3.v1, r3.v2};
 #pragma unroll
-                        for (int a = 0; a < NBA; ++a) {
-                            const float v = S.st[a].flat ? 1.0f : vv[a];
-                            maps[(size_t)S.slot[a] * max_rr + idx] = v;
-                            const unsigned long long k2 = peak_key(v, (uint32_t)idx);
-                            key[a] = k2 > key[a] ? k2 : key[a];
-                        }
+                        for (int a = 0; a < NBA; ++a) maps[(size_t)S.slot[a] * max_rr + idx] = __int_as_float(acc[a][b][2 * h + e]);
                     }
                 }
+        __syncwarp();
+        //      (2) One rolled loop normalises the warp's 16 x 24 tile in place, lanes along x (conflict-free, and the
+        //      accumulators are dead, so the template statistics fit in registers): OpenCV's FP64 formula, then the
+        //      running maximum per lane -- positions are visited in increasing flat index, so a strict '>' keeps
+        //      the first maximum like np.argmax.
+        {
+            double mean[NBA], norm[NBA];
+            int soff[NBA], flat[NBA];
+            float bv[NBA];
+            int bi[NBA];
+#pragma unroll
+            for (int a = 0; a < NBA; ++a) {
+                mean[a] = S.st[a].mean; norm[a] = S.st[a].norm; flat[a] = S.st[a].flat;
+                soff[a] = S.slot[a] * max_rr;
+                bv[a] = -INFINITY; bi[a] = -1;
+            }
+#pragma unroll 1
+            for (int p = lane; p < 16 * 24; p += 32) {
+                const int ty = p / 24, tx = p - ty * 24;
+                const int y = y0 + ty, x = x0 + tx - ab;
+                if (y < RH && x >= 0 && x < RW) {
+                    const int idx = y * RW + x;
+                    const double ws = (double)wsum[idx];
+                    const double wd = wden[idx];
+#pragma unroll
+                    for (int a = 0; a < NBA; ++a) {
+                        const int c = __float_as_int(maps[soff[a] + idx]);
+                        const double num = __dsub_rn((double)c, __dmul_rn(ws, mean[a]));
+                        const float v = flat[a] ? 1.0f : __double2float_rn(ncc_finish(num, __dmul_rn(wd, norm[a])));
+                        maps[soff[a] + idx] = v;
+                        if (v > bv[a]) { bv[a] = v; bi[a] = idx; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < NBA; ++a)
+                if (bi[a] >= 0) {
+                    const unsigned long long k2 = peak_key(bv[a], (uint32_t)bi[a]);
+                    key[a] = k2 > key[a] ? k2 : key[a];
+                }
+        }
     }
 #pragma unroll
     for (int a = 0; a < NBA; ++a) {
