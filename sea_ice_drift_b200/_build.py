@@ -26,17 +26,19 @@ def is_stale():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=None, extra=()):
+    """``out`` / ``extra``: build an experimental variant next to the product library, e.g.
+    ``build(force=True, out='/tmp/libsid_kstd.so', extra=['-DSID_IMMA_KSTD'])`` for an A/B run."""
+    if not force and not is_stale() and out is None:
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB, os.path.join(CSRC, "sid_api.cu")]
+    cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", out or LIB, os.path.join(CSRC, "sid_api.cu")]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout)
     if res.returncode:
         raise RuntimeError("nvcc failed (%d)" % res.returncode)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -82,9 +82,13 @@ struct PmArgs {
 };
 
 __host__ __device__ inline int pm_window_pitch_words(int W, bool imma = false) {
-    if (imma) {                           // pitch == 8 (mod 16) words: the 4 rows of a half-warp's LDS.64 tile all 32 banks
+    if (imma) {
         int w = (W + 4 + 3) / 4;
+#ifdef SID_IMMA_KSTD                      // candidate layout: pitch == 4 (mod 8) words, conflict-free scalar A loads
+        while ((w & 7) != 4) ++w;
+#else                                     // pitch == 8 (mod 16) words
         while ((w & 15) != 8) ++w;
+#endif
         return w;
     }
     int n16 = (W + 4 + 15) / 16;          // 16-byte units, with room for the shifted tail
@@ -255,7 +259,17 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
     const int g = lane >> 2, tig = lane & 3;
     const int nxg = (RW + ab + 23) / 24;               // tiles over shifted columns x' = x + ab (see pm_tiles)
     const int ntiles = ((RH + 15) >> 4) * nxg;
+#ifdef SID_IMMA_KSTD
+    // Candidate K mapping (not built by default; checked on the CPU by scratch/emulate_imma_layout.py): hardware K slot k
+    // holds window byte k, i.e. a lane's A words are tig and tig+4 -- with a pitch == 4 (mod 8) words the 8 rows x 4 lanes
+    // of a scalar load hit 32 distinct banks (the permuted mapping below always takes 2 wavefronts).  Its B words are two
+    // unaligned words 16 bytes apart: bytes (8 + 4*tig - g) and +16 of the padded template row.
+    const int ob = 8 + 4 * tig - g;
+    constexpr int A_LANE = 1, A_HI = 4, B_HI = 4;
+#else
     const int ob = 8 + 8 * tig - g;               // byte offset of this lane's B bytes inside a padded template row
+    constexpr int A_LANE = 2, A_HI = 1, B_HI = 1;
+#endif
     const int bw = ob >> 2, bsh = (ob & 3) * 8;
     unsigned long long key[NBA];
 #pragma unroll
@@ -270,7 +284,7 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
             for (int b = 0; b < 3; ++b)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[a][b][e] = 0;
-        const uint32_t *arow = win32 + (y0 + g) * wpw + (x0 >> 2) + 2 * tig;
+        const uint32_t *arow = win32 + (y0 + g) * wpw + (x0 >> 2) + A_LANE * tig;
         const uint32_t *trow = tpl32 + bw;
         const uint32_t *arow8 = arow + 8 * wpw;
         const int nc = NC > 0 ? NC : nc_rt;
@@ -285,14 +299,14 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
                 for (int b = 0; b < 3; ++b) {
                     af[b][0] = arow[8 * c + 2 * b];
                     af[b][1] = arow8[8 * c + 2 * b];
-                    af[b][2] = arow[8 * c + 2 * b + 1];
-                    af[b][3] = arow8[8 * c + 2 * b + 1];
+                    af[b][2] = arow[8 * c + 2 * b + A_HI];
+                    af[b][3] = arow8[8 * c + 2 * b + A_HI];
                 }
 #pragma unroll
                 for (int a = 0; a < NBA; ++a) {
                     const uint32_t *tr = trow + a * tstride + 8 * c;
-                    const uint32_t w0 = tr[0], w1 = tr[1], w2 = tr[2];
-                    const uint32_t b0 = __funnelshift_r(w0, w1, bsh), b1 = __funnelshift_r(w1, w2, bsh);
+                    const uint32_t w0 = tr[0], w1 = tr[1], w2 = tr[B_HI], w3 = tr[B_HI + 1];   // B_HI == 1: w2 is w1 again (one load)
+                    const uint32_t b0 = __funnelshift_r(w0, w1, bsh), b1 = __funnelshift_r(w2, w3, bsh);
 #pragma unroll
                     for (int b = 0; b < 3; ++b) mma_u8_16832(acc[a][b], af[b][0], af[b][1], af[b][2], af[b][3], b0, b1);
                 }
