@@ -260,7 +260,7 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
     const int nxg = (RW + ab + 23) / 24;               // tiles over shifted columns x' = x + ab (see pm_tiles)
     const int ntiles = ((RH + 15) >> 4) * nxg;
 #ifdef SID_IMMA_KSTD
-    // Candidate K mapping (not built by default; checked on the CPU by scratch/emulate_imma_layout.py): hardware K slot k
+    // Candidate K mapping (not built by default; checked on the CPU by tests/imma_layout_emulation.py): hardware K slot k
     // holds window byte k, i.e. a lane's A words are tig and tig+4 -- with a pitch == 4 (mod 8) words the 8 rows x 4 lanes
     // of a scalar load hit 32 distinct banks (the permuted mapping below always takes 2 wavefronts).  Its B words are two
     // unaligned words 16 bytes apart: bytes (8 + 4*tig - g) and +16 of the padded template row.

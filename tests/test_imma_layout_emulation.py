@@ -1,13 +1,7 @@
 """Host-side check of the tensor-core operand layouts of pm_tiles_imma: a NumPy emulation of the mma.sync.m16n8k32
-fragment ownership (scratch/emulate_imma_layout.py) must reproduce the direct correlation for the shipped ("perm") and
+fragment ownership (tests/imma_layout_emulation.py) must reproduce the direct correlation for the shipped ("perm") and
 the candidate ("std", -DSID_IMMA_KSTD) K mapping, and reports the shared-memory wavefronts of the A loads."""
-import importlib.util
-import os
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-spec = importlib.util.spec_from_file_location("emulate_imma_layout", os.path.join(ROOT, "scratch", "emulate_imma_layout.py"))
-emu = importlib.util.module_from_spec(spec)
-spec.loader.exec_module(emu)
+from tests import imma_layout_emulation as emu
 
 
 def test_both_layouts_reproduce_direct_correlation():

@@ -154,3 +154,13 @@ def test_two_rank_series_gather_equals_single_process():
         for t, w in zip(tables, want):
             assert np.array_equal(t, w, equal_nan=True)
         assert len(seen) == (3 if rank == 0 else 2)          # pairs 0,2,4 / 1,3 -- nothing computed twice
+
+
+def test_bind_rank_to_gpu_is_a_no_op_without_a_gpu():
+    import os
+    from sea_ice_drift_b200.sharding import bind_rank_to_gpu
+    before = os.sched_getaffinity(0)
+    cores = bind_rank_to_gpu(0)
+    assert cores is None or set(cores) <= before          # never widens the affinity, never raises
+    if cores is None:
+        assert os.sched_getaffinity(0) == before
