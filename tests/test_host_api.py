@@ -127,3 +127,15 @@ def test_user_template_matcher_plugin_is_detected():
     assert pmlib._is_builtin_matcher(None) and pmlib._is_builtin_matcher(cv2.matchTemplate)
     assert pmlib._is_builtin_matcher(sid.match_template)
     assert not pmlib._is_builtin_matcher(lambda img, tpl, m: None)
+
+
+def test_integration_snippet_angle_table_equals_binding():
+    """The angle table a reference maintainer builds in INTEGRATION.md section 2 is the one the binding passes."""
+    for img_size, alpha0, angles in ((35, 0.0, [-3, 0, 3]), (50, -3.85, [0.5, 7.25]), (51, 12.0, list(range(-10, 11)))):
+        tab = np.empty((len(angles), 4))
+        tc = np.array([int(img_size / 2.) + 1] * 2)
+        for k, ang in enumerate(np.asarray(angles, dtype=np.float64)):
+            a = np.radians(ang - alpha0)
+            T = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+            tab[k] = (T[0, 0], T[1, 0]) + tuple(tc.dot(T))
+        assert np.array_equal(tab, _lib.angle_table(angles, alpha0, img_size))
