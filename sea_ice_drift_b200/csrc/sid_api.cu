@@ -343,7 +343,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
 
 extern "C" {
 
-const char *sid_version(void) { return "sea_ice_drift_b200 0.1 (sm_100a, IDP.4A exact-integer MCC)"; }
+const char *sid_version(void) { return "sea_ice_drift_b200 0.2 (sm_100a, exact-integer u8 tensor-core MCC)"; }
 
 int sid_create(sid_ctx **out, int device) {
     if (!out) return SID_EINVAL;
@@ -528,7 +528,7 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
     for (int64_t i = 0; i < n; ++i) {
         const double b = border[i];
         int v = 0;
-        if (std::isfinite(b) && b >= 0.0 && b < 4096.0) v = (int)b;
+        if (std::isfinite(b) && b >= 0.0 && b < 4096.0) v = (int)std::ceil(b);   // fractional borders: the window can be one pixel wider
         ib[(size_t)i] = v;
         max_border = std::max(max_border, v);
         if (nbands > 1) {
@@ -720,7 +720,7 @@ int sid_run_device(sid_ctx *ctx, int64_t n, const double *d_c1, const double *d_
         CU(cudaMemcpyAsync(hb.data(), d_border, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         max_border = 1;
-        for (double b : hb) if (std::isfinite(b) && b >= 0.0 && b < 4096.0) max_border = std::max(max_border, (int)b);
+        for (double b : hb) if (std::isfinite(b) && b >= 0.0 && b < 4096.0) max_border = std::max(max_border, (int)std::ceil(b));
     }
     const double *d_angles, *d_tab;
     if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab))) return rc;

@@ -35,7 +35,7 @@ def interpolation_near(x1, y1, x2, y2, x1grd, y1grd, method='linear', **kwargs):
         # what griddata(method='linear') does, but with ONE Delaunay triangulation shared by both value
         # sets (the reference triangulates the same keypoints twice); values are identical
         both = LinearNDInterpolator(src, np.column_stack([x2, y2]), fill_value=np.nan)(dst)
-        return both[:, 0].T, both[:, 1].T
+        return both[..., 0].T, both[..., 1].T      # value axis is the last one for 1-D and 2-D grids alike
     return (griddata(src, x2, dst, method=method).T,
             griddata(src, y2, dst, method=method).T)
 

@@ -30,29 +30,9 @@ DEFAULT_SRS = '+proj=latlong +datum=WGS84 +ellps=WGS84 +no_defs'
 shared_args = None
 shared_kwargs = None
 
-_pair_cache = {}
-
-
 def _ctx(kwargs=None):
     device = None if not kwargs else kwargs.get('device')
     return _lib.default_context(device)
-
-
-def _pair_fingerprint(img):
-    a = np.asarray(img)
-    step = max(1, a.size // 4096)
-    # .flat[::step] visits only the sampled elements (reshape(-1) would copy a non-contiguous view)
-    return (a.__array_interface__['data'][0], a.shape, a.strides, int(a.flat[::step].sum(dtype=np.int64)))
-
-
-def _ensure_pair(ctx, img1, img2):
-    """Upload the pair unless the same arrays are already resident."""
-    key = (_pair_fingerprint(img1), _pair_fingerprint(img2))
-    if _pair_cache.get(id(ctx)) != key or ctx._pair_key != key:
-        ctx.set_pair(img1, img2)
-        ctx._pair_key = key
-        _pair_cache[id(ctx)] = key
-    return ctx
 
 
 def _is_builtin_matcher(fn):
@@ -78,10 +58,17 @@ def get_template(img, c, r, a, s, rot_order=0, **kwargs):
     return _ctx(kwargs).get_template(img, c, r, a, s, rot_order)
 
 
+try:                                        # the reference's default (pmlib.py:120); recognised and run on the GPU
+    import cv2 as _cv2
+    _DEFAULT_MATCHER = _cv2.matchTemplate
+except ImportError:                         # no OpenCV installed: same behaviour, our own callable as the default
+    _DEFAULT_MATCHER = match_template
+
+
 def rotate_and_match(img1, c1, r1, img_size, image2, alpha0,
                      angles=[-3, 0, 3],
                      mtype=TM_CCOEFF_NORMED,
-                     template_matcher=None,
+                     template_matcher=_DEFAULT_MATCHER,
                      mcc_norm=False,
                      **kwargs):
     """Best match of the rotated templates of one point inside ``image2``
@@ -121,7 +108,11 @@ def rotate_and_match(img1, c1, r1, img_size, image2, alpha0,
 def use_mcc_batch(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, **kwargs):
     """``use_mcc`` for every point at once: the body of the reference's Pool map
     (pmlib.py:436-448) as one fused kernel launch.  Returns an (N, 5) float64 table
-    ``c2, r2, angle, r, h`` with NaN rows where the reference returns NaN."""
+    ``c2, r2, angle, r, h`` with NaN rows where the reference returns NaN.
+
+    ``resident=True`` (extension): reuse the image pair uploaded by this context's previous call instead of
+    uploading ``img1`` / ``img2`` again -- an explicit contract, for callers that run several grids or kwargs
+    sets over one pair; raises nothing and uploads anyway when no pair is resident."""
     matcher = kwargs.get('template_matcher')
     if not _is_builtin_matcher(matcher):
         rows = [use_mcc(a, b, c, d, e, img1, img2, img_size, alpha0, **kwargs)
@@ -132,12 +123,14 @@ def use_mcc_batch(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, **kw
                               kwargs.get('mcc_norm', False))
     args = (c1, r1, c2fg, r2fg, border, img_size, list(kwargs.get('angles', [-3, 0, 3])), alpha0,
             kwargs.get('rot_order', 0), flags, kwargs.get('mtype', TM_CCOEFF_NORMED))
-    key = (_pair_fingerprint(img1), _pair_fingerprint(img2))
-    if _pair_cache.get(id(ctx)) == key and ctx._pair_key == key:
-        return ctx.run(*args)                      # pair already resident
-    out = ctx.run_pair(img1, img2, *args)          # upload overlapped with the matching
-    ctx._pair_key = key
-    _pair_cache[id(ctx)] = key
+    # The pair is uploaded on EVERY call (overlapped with the matching, so it costs ~1.5 ms per EW pair) unless
+    # the caller states explicitly that the pair of its previous call is still the one to match: the library
+    # never infers identity from pointers or sampled checksums (an in-place edit such as masking land, or a new
+    # array at a recycled address, would silently match against the old pair).
+    if kwargs.get('resident') and ctx._pair_key is not None:
+        return ctx.run(*args)
+    out = ctx.run_pair(img1, img2, *args)
+    ctx._pair_key = (np.shape(img1), np.shape(img2))
     return out
 
 

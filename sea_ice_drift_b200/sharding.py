@@ -47,6 +47,16 @@ def gather_rows(local_rows, local_idx, n_total, dist, device=None):
     return out
 
 
+def _collective_device(dist, device=None):
+    """Device the gather tensors live on: the compute context's GPU on NCCL (NOT torch's current device, which is
+    cuda:0 in every rank unless the caller set it), None / CPU on gloo."""
+    if dist.get_backend() != 'nccl':
+        return None
+    import torch
+    from . import _lib
+    return torch.device('cuda', _lib.default_context(device).device)
+
+
 def use_mcc_batch_sharded(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, compute=None, **kwargs):
     """``use_mcc_batch`` over all ranks of an initialised process group (falls back to
     a plain single-GPU call when there is none).  Every rank passes the same inputs
@@ -62,11 +72,7 @@ def use_mcc_batch_sharded(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alph
     idx = shard_indices(border, world, rank)
     arrs = [np.asarray(a, dtype=np.float64)[idx] for a in (c1, r1, c2fg, r2fg, border)]
     local = compute(*arrs, img1, img2, img_size, alpha0, **kwargs) if len(idx) else np.zeros((0, 5))
-    device = None
-    if dist.get_backend() == 'nccl':
-        import torch
-        device = torch.device('cuda', torch.cuda.current_device())
-    return gather_rows(local, idx, n, dist, device)
+    return gather_rows(local, idx, n, dist, _collective_device(dist, kwargs.get('device')))
 
 
 def shard_pairs(n_pairs, world_size, rank):
@@ -101,14 +107,17 @@ def use_mcc_series(pairs, img_size, alpha0=0.0, n_contexts=1, compute=None, gath
     n_contexts = max(1, min(int(n_contexts), max(1, len(mine))))
     if compute is None:
         from . import _lib
-        flags = _lib.flags_from_kwargs(kwargs)
+        # the reference's own defaults (pmlib.py:36, 118-121): hes_norm=True, hes_smth=False, mcc_norm=False
+        flags = _lib.flags_from_kwargs(kwargs.get('hes_norm', True), kwargs.get('hes_smth', False),
+                                       kwargs.get('mcc_norm', False))
         angles = kwargs.get('angles', [-3, 0, 3])
         rot_order = kwargs.get('rot_order', 0)
+        mtype = kwargs.get('mtype', _lib.SID_TM_CCOEFF_NORMED)
         ctxs = [_lib.default_context()] + [_lib.Context(_lib.default_context().device) for _ in range(n_contexts - 1)]
 
         def compute(slot, img1, img2, c1, r1, c2fg, r2fg, border):
             return ctxs[slot].run_pair(img1, img2, c1, r1, c2fg, r2fg, border, img_size, angles, alpha0,
-                                       rot_order=rot_order, flags=flags)
+                                       rot_order=rot_order, flags=flags, mtype=mtype)
     work = queue.Queue()
     for k in mine:
         work.put(k)
@@ -161,7 +170,7 @@ def _gather_series(results, mine, n_pairs, dist, root_only=False):
     NCCL the tables travel host -> device -> all ranks -> host through cached pinned staging buffers."""
     import torch
     world = dist.get_world_size()
-    device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    device = _collective_device(dist) or torch.device('cpu')
     per_rank = -(-n_pairs // world)
     sizes = torch.full((per_rank,), -1, dtype=torch.int64)
     for j, k in enumerate(mine):
@@ -183,7 +192,7 @@ def _gather_series(results, mine, n_pairs, dist, root_only=False):
     host = _staging('recv', (world, per_rank, n_max, 5), device)
     host.copy_(gathered.view(world, per_rank, n_max, 5), non_blocking=True)
     if device.type == 'cuda':
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(device).synchronize()
     g = host.numpy()
     out = [None] * n_pairs
     for r in range(world):
