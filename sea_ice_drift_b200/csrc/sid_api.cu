@@ -15,6 +15,7 @@
 #include "../../include/sid_b200.h"
 #include "sid_common.cuh"
 #include "sid_pm_kernel.cuh"
+#include "sid_pm_tc_kernel.cuh"
 #include "sid_single_kernels.cuh"
 #include "sid_knn_kernel.cuh"
 #include "sid_defor_kernel.cuh"
@@ -198,12 +199,40 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     a.out = d_out; a.status = d_status;
     a.max_rr = Rmax * Rmax;
     a.max_hrw = Wmax * Rmax;
-    // correlation path: tensor cores (IMMA, exact u8 x u8 -> s32) unless SID_PM_PATH=dp4a
+    // correlation path: tcgen05 tensor cores (default), legacy mma.sync (SID_PM_PATH=imma) or the integer pipe
+    // (SID_PM_PATH=dp4a); all three give bit-identical results
     const char *path_env = getenv("SID_PM_PATH");
+    const bool want_tc = !path_env || strcmp(path_env, "tc") == 0;
     const bool imma = !(path_env && strcmp(path_env, "dp4a") == 0);
+    const bool smth = (flags & SID_HES_SMTH) != 0;
+    // Split tail: peak statistics in a second, light kernel when the result map fits its shared memory
+    bool split_tail = pm_tail_smem_bytes(a.max_rr, smth) <= 52 * 1024;       // >= 4 tail CTAs per SM; larger maps measured
+                                                                             // faster with the fused tail (cfg1: 1.10 vs 1.21 ms)
+    if (const char *e = getenv("SID_PM_SPLIT_TAIL")) if (e[0] == '0') split_tail = false;
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    PmTcCfg tg;
+    memset(&tg, 0, sizeof tg);
+    bool use_tc = false;
+    if (want_tc && pm_tc_geometry(s, Rmax, Wmax, n_angles, tg) && make_window_tensor_map(ctx, &tmap, 16, tg.load_rows)) use_tc = true;
+    bool smem_scratch = false;
+    size_t smem = 0;
+    int variant = 0;
+    if (use_tc) {
+        // window panels + four byte-shifted copies of the template rows (+ the per-point scratch when two CTAs
+        // still fit on an SM)
+        a.tma = 1;
+        a.ab = tg.nab;
+        const size_t base = (size_t)tg.win_bytes + (size_t)tg.tpl_bytes;
+        const size_t need = base + pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab, smth, split_tail);
+        const size_t cap2 = 108 * 1024;
+        if (need <= cap2 && !getenv("SID_PM_GLOBAL_SCRATCH")) { smem_scratch = true; smem = need; }
+        else smem = base;
+        if (smem > (size_t)ctx->max_smem_optin - 4096) use_tc = false;      // window too large: legacy kernels
+    }
+    if (!use_tc) {
     // window staging by TMA when the padded window (+15 bytes: the box must start 16-byte aligned) fits one
     // box of <= 256 x 256 bytes
-    alignas(64) CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     a.tma = 0;
     int wpw = pm_window_pitch_words(Wmax, imma);
@@ -217,8 +246,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     }
     a.win_words = (Wmax + (imma ? PM_IMMA_ROW_SLACK : 0)) * wpw + PM_WIN_SLACK;
     const int nw = (s + 3) / 4;
-    int variant;                      // dp4a kernel specialisation by template width in words
-    if (nw == 9) variant = 0; else if (nw == 13) variant = 1; else variant = 2;
+    if (nw == 9) variant = 0; else if (nw == 13) variant = 1; else variant = 2;   // dp4a kernel specialisation by template width in words
     if (imma) {
         a.nc = (s + 7 + 31) / 32;
         a.tpw = (32 * a.nc + 16) / 4;
@@ -230,16 +258,9 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         a.tpl_off = 0;
         a.ab = std::min(n_angles, PM_MAX_AB);
     }
-    // Split tail: peak statistics in a second, light kernel when the result map fits its shared memory
-    const bool smth = (flags & SID_HES_SMTH) != 0;
-    bool split_tail = pm_tail_smem_bytes(a.max_rr, smth) <= 52 * 1024;       // >= 4 tail CTAs per SM; larger maps measured
-                                                                             // faster with the fused tail (cfg1: 1.10 vs 1.21 ms)
-    if (const char *e = getenv("SID_PM_SPLIT_TAIL")) if (e[0] == '0') split_tail = false;
     // Shared memory: window + templates (+ the per-point scratch when it all fits in a third of an SM).
     const size_t smem_cap_fast = 75 * 1024;
     auto base_smem = [&](int ab) { return ((size_t)a.win_words + (size_t)ab * s * a.tpw) * 4; };
-    bool smem_scratch = false;
-    size_t smem = 0;
     for (int ab = a.ab; ab >= 1 && !smem_scratch; --ab) {
         const size_t need = base_smem(ab) + pm_scratch_bytes(a.max_rr, a.max_hrw, ab, smth, split_tail);
         // fewer resident templates only pays if it keeps all angles in <= the same number of batches
@@ -254,11 +275,14 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         if (smem > (size_t)ctx->max_smem_optin)
             return fail(ctx, SID_EUNSUPPORTED, "search window too large for the fused kernel (border too big)");
     }
+    }
 
     // CTA size: fill the CTA with thread tiles (dp4a) / warp tiles (IMMA) of a typical point
     const int Rt = 2 * typ_border + (Wmax - 2 * max_border) - s + 1;
     int threads = PM_THREADS;
-    if (imma) {
+    if (use_tc) {
+        threads = TC_THREADS;
+    } else if (imma) {
         const int warp_tiles = ((Rt + 15) / 16) * ((Rt + 23) / 24);
         double best_eff = -1.0;
         for (int w = 4; w <= PM_IMMA_THREADS / 32; ++w) {
@@ -277,7 +301,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
             if (eff >= best_eff - 1e-9) { best_eff = eff; threads = bs; }
         }
     }
-    if (const char *e = getenv("SID_PM_THREADS")) {
+    if (const char *e = use_tc ? nullptr : getenv("SID_PM_THREADS")) {
         const int v = atoi(e);
         if (v >= 32 && v <= (imma ? PM_IMMA_THREADS : PM_THREADS) && v % 32 == 0) threads = v;
     }
@@ -286,8 +310,8 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
                            (const void *)pm_points_kernel<0, false, false>, (const void *)pm_points_kernel<9, true, false>,
                            (const void *)pm_points_kernel<13, true, false>, (const void *)pm_points_kernel<0, true, false>,
                            (const void *)pm_points_kernel<0, false, true>, (const void *)pm_points_kernel<0, true, true>};
-    const int kidx = imma ? (smem_scratch ? 7 : 6) : variant + (smem_scratch ? 3 : 0);
-    const void *kfn = ktab[kidx];
+    const int kidx = use_tc ? (smem_scratch ? 9 : 8) : imma ? (smem_scratch ? 7 : 6) : variant + (smem_scratch ? 3 : 0);
+    const void *kfn = use_tc ? (smem_scratch ? (const void *)pm_tc_kernel<true> : (const void *)pm_tc_kernel<false>) : ktab[kidx];
     if (int arc = allow_max_smem(ctx, kfn)) return arc;
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
@@ -297,6 +321,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
                  "%d angles/batch, tma %d)", kidx, threads, smem, s, max_border, a.ab, a.tma);
         return fail(ctx, SID_ECUDA, msg);
     }
+    if (use_tc) occ = std::min(occ, 512 / tg.tmem_cols);       // tensor memory: 512 columns per SM
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > n) grid = n;
     if (grid < 1) grid = 1;
@@ -322,7 +347,9 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.max_rr;
         a.tail_recs = (PmTailRec *)ctx->tail_recs.p + tail_off;
     }
-    void *params[] = {(void *)&a, (void *)&tmap};
+    void *params_legacy[] = {(void *)&a, (void *)&tmap};
+    void *params_tc[] = {(void *)&a, (void *)&tg, (void *)&tmap};
+    void **params = use_tc ? params_tc : params_legacy;
     if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
     CU(cudaEventRecord(ctx->k_ev[0], st));
     CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, st));
