@@ -224,10 +224,24 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         a.tma = 1;
         a.ab = tg.nab;
         const size_t base = (size_t)tg.win_bytes + (size_t)tg.tpl_bytes;
-        const size_t need = base + pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab, smth, split_tail);
+        const size_t scratch = pm_scratch_bytes(a.max_rr, a.max_hrw, a.ab, smth, split_tail);
+        const size_t wsq_bytes = ((size_t)a.max_rr * 4 + 255) & ~(size_t)255;
+        const size_t need = base + scratch + wsq_bytes;
         const size_t cap2 = 108 * 1024;
         if (need <= cap2 && !getenv("SID_PM_GLOBAL_SCRATCH")) { smem_scratch = true; smem = need; }
         else smem = base;
+        // window sums on the tensor cores: the two squares windows alias the result maps (dead until the first
+        // epilogue), two accumulators of n16hmax columns + two A slots must fit the tensor-memory allocation
+        if (smem_scratch) {
+            const size_t maps_off = ((size_t)a.max_rr * 12 + 127) & ~(size_t)127;
+            const size_t sq_bytes = 2 * (size_t)tg.npanels * (size_t)tg.wrows * 16;
+            const bool fits_smem = maps_off + sq_bytes <= scratch;
+            const bool fits_tmem = 2 * tg.n16hmax + 8 <= tg.nacc * tg.n16max + tg.slotc && tg.n16hmax <= tg.wrows;
+            const char *e = getenv("SID_TC_MMA_SUMS");
+            if (fits_smem && fits_tmem && !(e && e[0] == '0')) {
+                tg.mma_sums = 1; tg.sq_off = (int)maps_off; tg.wsq_off = (int)scratch;
+            }
+        }
         if (smem > (size_t)ctx->max_smem_optin - 4096) use_tc = false;      // window too large: legacy kernels
     }
     if (!use_tc) {
@@ -321,7 +335,22 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
                  "%d angles/batch, tma %d)", kidx, threads, smem, s, max_border, a.ab, a.tma);
         return fail(ctx, SID_ECUDA, msg);
     }
-    if (use_tc) occ = std::min(occ, 512 / tg.tmem_cols);       // tensor memory: 512 columns per SM
+    if (getenv("SID_DEBUG"))
+        fprintf(stderr, "[sid] launch: tc=%d kidx=%d threads=%d smem=%zu occ(api)=%d tmem_cols=%d nab=%d ks=%d nacc=%d nb8=%d slotc=%d n16max=%d wrows=%d npanels=%d\n",
+                (int)use_tc, kidx, threads, smem, occ, tg.tmem_cols, tg.nab, tg.ks, tg.nacc, tg.nb8, tg.slotc, tg.n16max, tg.wrows, tg.npanels);
+    if (use_tc) {
+        // The occupancy API answers 1 for a kernel that executes tcgen05.alloc with a run-time column count (it has to
+        // assume all 512 columns); residency is really bounded by registers, shared memory and the columns we ask for.
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, kfn));
+        int smem_sm = 0, regs_sm = 0;
+        CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+        CU(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, ctx->device));
+        const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
+        const int by_regs = regs_sm / std::max(1, fa.numRegs * threads);
+        occ = std::max(1, std::min(std::min(by_smem, by_regs), 512 / tg.tmem_cols));
+    }
+    if (const char *e = getenv("SID_PM_OCC")) { const int v = atoi(e); if (v >= 1 && v <= occ) occ = v; }
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > n) grid = n;
     if (grid < 1) grid = 1;

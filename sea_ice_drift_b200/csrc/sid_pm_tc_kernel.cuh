@@ -52,6 +52,11 @@ struct PmTcCfg {
     int tpw;        // words per template-row copy
     int tang;       // bytes per angle in the template area
     int win_bytes, tpl_bytes;
+    // window sums on the tensor cores (set by the host when shared memory / tensor memory allow it)
+    int mma_sums;   // 1: horizontal box sums of v and v^2 by a ones-Toeplitz MMA, vertical sums from TMEM rows
+    int n16hmax;    // accumulator width of those MMAs: window rows rounded up to 16
+    int sq_off;     // byte offset (from the scratch slab) of the two squares windows (alias the result maps)
+    int wsq_off;    // byte offset (from the scratch slab) of the u32 sums of squares
 };
 
 inline bool pm_tc_geometry(int s, int Rmax, int Wmax, int n_angles, PmTcCfg &g) {
@@ -80,8 +85,8 @@ inline bool pm_tc_geometry(int s, int Rmax, int Wmax, int n_angles, PmTcCfg &g) 
     if (need > 512) return false;
     g.tmem_cols = 32;
     while (g.tmem_cols < need) g.tmem_cols <<= 1;
-    g.wrows = (s + g.n16max + 7) & ~7;
-    if (g.wrows < Wmax) g.wrows = (Wmax + 7) & ~7;
+    g.wrows = (s + g.n16max + 15) & ~15;                          // >= window rows rounded up to 16 (N of the sums MMAs)
+    if (g.wrows < Wmax) g.wrows = (Wmax + 15) & ~15;
     const int ntiles = (Rmax + g.xt - 1) / g.xt;
     g.np_load = (Wmax + 15 + 15) / 16;
     const int p0max = ((ntiles - 1) * g.xt + 15) >> 4;
@@ -90,7 +95,10 @@ inline bool pm_tc_geometry(int s, int Rmax, int Wmax, int n_angles, PmTcCfg &g) 
     g.load_rows = Wmax;
     g.win_bytes = g.npanels * g.wrows * 16;
     g.tang = s * 4 * g.tpw * 4 + 16;
-    g.tpl_bytes = (g.nab * g.tang + 4 * g.tpw * 4 + 127) & ~127;    // + one row of slack behind the last angle
+    // behind the last angle: a row of zeros (dead lanes), a row of ones and a row of 255s (window sums), 4 copies each
+    g.tpl_bytes = (g.nab * g.tang + 12 * g.tpw * 4 + 127) & ~127;
+    g.n16hmax = (Wmax + 15) & ~15;
+    g.mma_sums = 0; g.sq_off = 0; g.wsq_off = 0;
     return true;
 }
 
@@ -131,6 +139,18 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo, u
 }
 // instruction descriptor: D = s32, A = B = u8, both K-major, M = 128
 __device__ __forceinline__ uint32_t tc_idesc_u8(int n) { return (2u << 4) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
 // the 128 threads of one warp group (barrier 1 or 2; 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync_group(int wg) {
     if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -144,6 +164,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
     __shared__ PmShared S;
     __shared__ __align__(8) unsigned long long win_bar, slot_bar[6], done_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint16_t sq_lut[256];                            // v -> (v*v / 255) << 8 | (v*v % 255)
     unsigned win_phase = 0, done_phase = 0, slot_par = 0;       // slot_par: bit b = parity of completed phases of slot_bar[b]
     const int tid = threadIdx.x, lane = tid & 31, nt = TC_THREADS;
     const int wg = tid >> 7, wiw = (tid >> 5) & 3;              // warp group, warp in group == TMEM lane quarter
@@ -161,8 +182,19 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
     float *maps = reinterpret_cast<float *>(wsum + a.max_rr);
     uint32_t *hs = reinterpret_cast<uint32_t *>(maps);
     uint32_t *hq = hs + a.max_hrw;
+    uint8_t *sR = slab + g.sq_off, *sD = sR + (size_t)g.npanels * PS;      // squares windows: v^2 = 255 * d + r (mma_sums only)
+    uint32_t *wsq = reinterpret_cast<uint32_t *>(slab + g.wsq_off);
 
     for (int t = tid; t < g.tpl_bytes / 4; t += nt) reinterpret_cast<uint32_t *>(sT)[t] = 0u;   // the padding stays zero for good
+    {
+        const uint32_t x = (uint32_t)tid * (uint32_t)tid, d = (x + 1u + (x >> 8)) >> 8;          // exact x / 255 for x < 65536
+        sq_lut[tid] = (uint16_t)((d << 8) | (x - 255u * d));
+    }
+    __syncthreads();
+    for (int t = tid; t < 8 * s; t += nt) {                      // constant rows: `s` bytes of 1 / of 255, byte-shifted copies
+        const int j = t % s, c = (t / s) & 3, which = t / (4 * s);
+        sT[(size_t)nab * g.tang + (size_t)(4 + 4 * which + c) * tpw4 + 4 * g.ctlw + c + j] = which ? 255 : 1;
+    }
     if (tid == 0) {
         S.next = atomicAdd(a.counter, 1u);
         S.tma_for = 0xffffffffu;
@@ -238,43 +270,157 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
         if (!prefetched) { mbar_wait(&win_bar, win_phase); win_phase ^= 1u; }
         __syncthreads();
 
-        // ---- 2a. horizontal sliding sums over the template width, every window row
-        {
-            int seg = PM_SEG;
-            while (H * ((RW + seg - 1) / seg) > nt && seg < RW) ++seg;
-            const int nseg = (RW + seg - 1) / seg;
-            for (int t = tid; t < H * nseg; t += nt) {
-                const int y = t / nseg, xs = (t - y * nseg) * seg;
-                const int xe = min(RW, xs + seg);
-                const unsigned char *rowp = sW + y * 16;
-                auto wb = [&](int k) -> uint32_t { const int kk = k + xoff; return rowp[(kk >> 4) * PS + (kk & 15)]; };
-                uint32_t sum = 0, sq = 0;
-                for (int j = 0; j < s; ++j) { const uint32_t v = wb(xs + j); sum += v; sq += v * v; }
-                for (int x = xs; x < xe; ++x) {
-                    hs[y * RW + x] = sum; hq[y * RW + x] = sq;
-                    const uint32_t va = wb(x), vb = wb(x + s);
-                    sum += vb - va; sq += vb * vb - va * va;
+        if (g.mma_sums) {
+            // ---- 2 (tensor cores).  Horizontal box sums of every window row as ONE Toeplitz MMA per quantity:
+            //      Hs[x][r] = sum_k Ones[x][k] * W[r][k],   Hq[x][r] = sum_k Ones[x][k] * R[r][k] + 255s[x][k] * D[r][k]
+            //      with v^2 = 255 * D + R split into two bytes (exact), then the vertical sliding sums run along each
+            //      lane's own TMEM row (columns = window rows) in registers.
+            for (int t = tid; t < g.np_load * H * 4; t += nt) {
+                const int w = t & 3, u = t >> 2, r = u % H, pnl = u / H;
+                const int off = pnl * PS + r * 16 + 4 * w;
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(sW + off);
+                const uint32_t t0 = sq_lut[v & 255u], t1 = sq_lut[(v >> 8) & 255u], t2 = sq_lut[(v >> 16) & 255u], t3 = sq_lut[v >> 24];
+                *reinterpret_cast<uint32_t *>(sR + off) = __byte_perm(__byte_perm(t0, t1, 0x0040), __byte_perm(t2, t3, 0x0040), 0x5410);
+                *reinterpret_cast<uint32_t *>(sD + off) = __byte_perm(__byte_perm(t0, t1, 0x0051), __byte_perm(t2, t3, 0x0051), 0x5410);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+            const int n16h = (H + 15) & ~15;
+            const uint32_t idesc_h = tc_idesc_u8(n16h);
+            const uint32_t tQ = tD + (uint32_t)g.n16hmax;                    // second accumulator: sums of squares
+            const uint32_t tOnes = tA + (uint32_t)g.slotc, t255 = tA + (uint32_t)(2 * g.slotc);
+            const int ntile_s = (RW + g.xt - 1) / g.xt;
+            for (int tile = 0; tile < ntile_s; ++tile) {
+                const int xbase = tile * g.xt;
+                const int RWt = min(g.xt, RW - xbase);
+                const int col0 = xbase + xoff, p0 = col0 >> 4, offt = col0 & 15;
+                const int q = xi + offt;
+                const int cw0 = (xi_min + offt) >> 2;
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
+                {   // clear accumulators and slots
+                    uint32_t z[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) z[c] = 0u;
+                    const int ncol = g.nacc * g.n16max + 3 * g.slotc, half = ((ncol / 8 + 1) / 2) * 8;
+                    const int cb = wg * half, ce = min(ncol, cb + half);
+                    for (int c = cb; c < ce; c += 8) tc_st8(tD + lane_base + c, z);
+                    tc_st_wait();
+                    tc_fence_before();
+                }
+                __syncthreads();
+                tc_fence_after();
+                {   // warp group 0 writes the ones band, warp group 1 the 255s band (dead lanes: zeros)
+                    const uint32_t *p = xi < RWt
+                        ? reinterpret_cast<const uint32_t *>(sT + (size_t)nab * g.tang + (size_t)(4 + 4 * wg + (q & 3)) * tpw4) + g.ctlw - (q >> 2) + cw0
+                        : reinterpret_cast<const uint32_t *>(sT + (size_t)nab * g.tang);
+                    const uint32_t ta = (wg ? t255 : tOnes) + lane_base + (uint32_t)cw0;
+                    for (int grp = 0; grp < g.nb8; ++grp) {
+                        uint32_t v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) v[c] = p[grp * 8 + c];
+                        tc_st8(ta + grp * 8, v);
+                    }
+                    tc_st_wait();
+                    tc_fence_before();
+                }
+                __syncthreads();
+                if (lane == 0 && wiw < g.nissue) {
+                    tc_fence_after();
+                    const uint64_t toff = (uint64_t)((p0 * PS) >> 4);
+                    const uint64_t dW = bdesc0 + toff;
+                    const uint64_t dR = tc_smem_desc(smem_u32(sR), (uint32_t)PS, 128u) + toff;
+                    const uint64_t dD = tc_smem_desc(smem_u32(sD), (uint32_t)PS, 128u) + toff;
+                    for (int ks = wiw; ks < g.ks; ks += 4) {
+                        const uint64_t kso = (uint64_t)(ks * ((2 * PS) >> 4));
+                        if (wg == 0) {
+                            tc_mma_i8_ts(tD, tOnes + (uint32_t)(ks * 8), dW + kso, idesc_h, 1u);
+                        } else {
+                            tc_mma_i8_ts(tQ, tOnes + (uint32_t)(ks * 8), dR + kso, idesc_h, 1u);
+                            tc_mma_i8_ts(tQ, t255 + (uint32_t)(ks * 8), dD + kso, idesc_h, 1u);
+                        }
+                    }
+                    tc_commit(&done_bar[wg]);
+                }
+                mbar_wait(&done_bar[0], done_phase);
+                mbar_wait(&done_bar[1], done_phase);
+                done_phase ^= 1u;
+                tc_fence_after();
+                {   // vertical sliding sums along the lane's TMEM row; each warp group takes half of the output rows
+                    const int yh = (RH + 1) / 2, ys = wg * yh, ye = min(RH, ys + yh);
+                    const bool emit = xi < RWt && aa == 0;
+                    const int x = xbase + xi;
+                    if (ys < ye) {
+                        uint32_t sum = 0, sq = 0;
+                        for (int c0 = 0; c0 < s; c0 += 8) {
+                            uint32_t va[8], vb[8];
+                            tc_ld8(tD + lane_base + (uint32_t)(ys + c0), va);
+                            tc_ld8(tQ + lane_base + (uint32_t)(ys + c0), vb);
+                            tc_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) if (c0 + c < s) { sum += va[c]; sq += vb[c]; }
+                        }
+                        if (emit) { wsum[ys * RW + x] = sum; wsq[ys * RW + x] = sq; }
+                        for (int c0 = 0; ys + 1 + c0 < ye; c0 += 8) {
+                            uint32_t na[8], oa[8], nq[8], oq[8];
+                            tc_ld8(tD + lane_base + (uint32_t)(ys + s + c0), na);
+                            tc_ld8(tD + lane_base + (uint32_t)(ys + c0), oa);
+                            tc_ld8(tQ + lane_base + (uint32_t)(ys + s + c0), nq);
+                            tc_ld8(tQ + lane_base + (uint32_t)(ys + c0), oq);
+                            tc_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const int y = ys + 1 + c0 + c;
+                                sum += na[c] - oa[c]; sq += nq[c] - oq[c];
+                                if (emit && y < ye) { wsum[y * RW + x] = sum; wsq[y * RW + x] = sq; }
+                            }
+                        }
+                    }
                 }
             }
-        }
-        __syncthreads();
-        // ---- 2b. vertical sliding sums -> window sum and denominator per displacement
-        {
-            int vseg = PM_VSEG;
-            while (RW * ((RH + vseg - 1) / vseg) > nt && vseg < RH) ++vseg;
-            const int nseg = (RH + vseg - 1) / vseg;
-            for (int t = tid; t < RW * nseg; t += nt) {
-                const int sg = t / RW, x = t - sg * RW;
-                const int ys = sg * vseg, ye = min(RH, ys + vseg);
-                uint32_t sum = 0, sq = 0;
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            for (int idx = tid; idx < RR; idx += nt) wden[idx] = window_den(wsum[idx], wsq[idx], a.inv_area);
+        } else {
+        // ---- 2a. horizontal sliding sums over the template width, every window row
+            {
+                int seg = PM_SEG;
+                while (H * ((RW + seg - 1) / seg) > nt && seg < RW) ++seg;
+                const int nseg = (RW + seg - 1) / seg;
+                for (int t = tid; t < H * nseg; t += nt) {
+                    const int y = t / nseg, xs = (t - y * nseg) * seg;
+                    const int xe = min(RW, xs + seg);
+                    const unsigned char *rowp = sW + y * 16;
+                    auto wb = [&](int k) -> uint32_t { const int kk = k + xoff; return rowp[(kk >> 4) * PS + (kk & 15)]; };
+                    uint32_t sum = 0, sq = 0;
+                    for (int j = 0; j < s; ++j) { const uint32_t v = wb(xs + j); sum += v; sq += v * v; }
+                    for (int x = xs; x < xe; ++x) {
+                        hs[y * RW + x] = sum; hq[y * RW + x] = sq;
+                        const uint32_t va = wb(x), vb = wb(x + s);
+                        sum += vb - va; sq += vb * vb - va * va;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- 2b. vertical sliding sums -> window sum and denominator per displacement
+            {
+                int vseg = PM_VSEG;
+                while (RW * ((RH + vseg - 1) / vseg) > nt && vseg < RH) ++vseg;
+                const int nseg = (RH + vseg - 1) / vseg;
+                for (int t = tid; t < RW * nseg; t += nt) {
+                    const int sg = t / RW, x = t - sg * RW;
+                    const int ys = sg * vseg, ye = min(RH, ys + vseg);
+                    uint32_t sum = 0, sq = 0;
 #pragma unroll 5
-                for (int i = 0; i < s; ++i) { sum += hs[(ys + i) * RW + x]; sq += hq[(ys + i) * RW + x]; }
-                for (int y = ys; y < ye; ++y) {
-                    wsum[y * RW + x] = sum;
-                    wden[y * RW + x] = window_den(sum, sq, a.inv_area);
-                    if (y + 1 < ye) {
-                        sum += hs[(y + s) * RW + x] - hs[y * RW + x];
-                        sq += hq[(y + s) * RW + x] - hq[y * RW + x];
+                    for (int i = 0; i < s; ++i) { sum += hs[(ys + i) * RW + x]; sq += hq[(ys + i) * RW + x]; }
+                    for (int y = ys; y < ye; ++y) {
+                        wsum[y * RW + x] = sum;
+                        wden[y * RW + x] = window_den(sum, sq, a.inv_area);
+                        if (y + 1 < ye) {
+                            sum += hs[(y + s) * RW + x] - hs[y * RW + x];
+                            sq += hq[(y + s) * RW + x] - hq[y * RW + x];
+                        }
                     }
                 }
             }
@@ -308,31 +454,34 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                     const double jsn = __dmul_rn(dj, sn), jcs = __dmul_rn(dj, cs);
                     unsigned char *tdst = sT + (size_t)ai * g.tang + 4 * g.ctlw + gj;
                     uint32_t lsum = 0, lsq = 0; int lzero = 0;
+                    // each thread owns column gj and rows gi, gi + rows_per_pass, ...: U rows, four loads in flight at a
+                    // time, the remainder one by one (no predicated-off copies of the body)
+                    const int U = (s + rows_per_pass - 1) / rows_per_pass;
                     auto sweep = [&](auto sample) {
-                        for (int i0 = 0; i0 < s; i0 += 4 * rows_per_pass) {
+                        auto load = [&](int i) -> uint32_t {
+                            if (!(active && i < s)) return 1u;
+                            const double di = (double)i;
+                            const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), jsn);
+                            const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), jcs);
+                            return sample(row, col);
+                        };
+                        auto store = [&](int i, uint32_t v) {
+                            if (active && i < s) {
+                                unsigned char *d = tdst + (size_t)i * 4 * tpw4;
+                                const unsigned char b = (unsigned char)v;
+                                d[0] = b; d[tpw4 + 1] = b; d[2 * tpw4 + 2] = b; d[3 * tpw4 + 3] = b;
+                                lsum += v; lsq += v * v; lzero |= (v == 0);
+                            }
+                        };
+                        int u = 0;
+                        for (; u + 4 <= U; u += 4) {
                             uint32_t v[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = i0 + u * rows_per_pass + gi;
-                                v[u] = 1u;
-                                if (active && i < s) {
-                                    const double di = (double)i;
-                                    const double row = __dadd_rn(__dadd_rn(off0, __dmul_rn(di, cs)), jsn);
-                                    const double col = __dadd_rn(__dadd_rn(off1, __dmul_rn(di, -sn)), jcs);
-                                    v[u] = sample(row, col);
-                                }
-                            }
+                            for (int w = 0; w < 4; ++w) v[w] = load((u + w) * rows_per_pass + gi);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = i0 + u * rows_per_pass + gi;
-                                if (active && i < s) {
-                                    unsigned char *d = tdst + (size_t)i * 4 * tpw4;
-                                    const unsigned char b = (unsigned char)v[u];
-                                    d[0] = b; d[tpw4 + 1] = b; d[2 * tpw4 + 2] = b; d[3 * tpw4 + 3] = b;
-                                    lsum += v[u]; lsq += v[u] * v[u]; lzero |= (v[u] == 0);
-                                }
-                            }
+                            for (int w = 0; w < 4; ++w) store((u + w) * rows_per_pass + gi, v[w]);
                         }
+                        for (; u < U; ++u) store(u * rows_per_pass + gi, load(u * rows_per_pass + gi));
                     };
                     if (fast0) sweep([&](double row, double col) { return template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0); });
                     else if (inside) sweep([&](double row, double col) { return template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 1); });
@@ -392,31 +541,48 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                 }
                 __syncthreads();
                 tc_fence_after();
-                const uint64_t bdesc_t = bdesc0 + (uint64_t)((p0 * PS) >> 4);
-                for (int i = wg; i < s; i += 2) {
-                    const int slot = i % 3, bi = i % 6;
-                    if (i >= 3) {                                // MMAs of row i-3 (same slot, other warp group) are done?
-                        const int bw = (i - 3) % 6, kidx = (i - 3) / 6;
-                        mbar_wait(&slot_bar[bw], ((slot_par >> bw) + (unsigned)kidx) & 1u);
-                        tc_fence_after();
-                    }
-                    const uint32_t *p = trow + (size_t)i * 4 * g.tpw;
-                    const uint32_t ta = tA + lane_base + (uint32_t)(slot * g.slotc + cw0);
-                    for (int grp = 0; grp < g.nb8; ++grp) {
-                        uint32_t v[8];
+                // Row loop.  All index arithmetic is carried in running variables (i advances by 2): slot = i % 3,
+                // bi = i % 6 (the slot barrier this row commits to), bw = (i - 3) % 6 / kidx = (i - 3) / 6 (the barrier
+                // and completion index of the row that used this slot before).  Dead lanes read a row of zeros.
+                {
+                    const bool issuer = lane == 0 && wiw < g.nissue;
+                    const uint32_t sbar = smem_u32(&slot_bar[0]);
+                    const int row_words = 4 * g.tpw;
+                    const uint32_t *p = live ? trow + (size_t)wg * row_words
+                                             : reinterpret_cast<const uint32_t *>(sT + (size_t)nab * g.tang);
+                    const int pstep = live ? 2 * row_words : 0;
+                    // this thread's first MMA of a row (K step wiw); further K steps (ks >= 4) are rare
+                    const uint32_t d0 = tD + (uint32_t)((wiw % g.nacc) * g.n16max);
+                    const uint64_t b0 = bdesc0 + (uint64_t)((p0 * PS) >> 4) + (uint64_t)(wiw * ((2 * PS) >> 4));
+                    int slot = wg, bi = wg, bw = wg + 3, kidx = -1;       // state for i = wg
+                    for (int i = wg; i < s; i += 2) {
+                        if (i >= 3) {                            // MMAs of row i-3 (same slot, other warp group) done?
+                            mbar_wait_addr(sbar + 8u * (uint32_t)bw, ((slot_par >> bw) + (unsigned)kidx) & 1u);
+                            tc_fence_after();
+                        }
+                        const uint32_t ta = tA + lane_base + (uint32_t)(slot * g.slotc + cw0);
+                        for (int grp = 0; grp < g.nb8; ++grp) {
+                            uint32_t v[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) v[c] = live ? p[grp * 8 + c] : 0u;
-                        tc_st8(ta + grp * 8, v);
-                    }
-                    tc_st_wait();
-                    tc_fence_before();
-                    bar_sync_group(wg);
-                    if (lane == 0 && wiw < g.nissue) {
-                        tc_fence_after();
-                        for (int ks = wiw; ks < g.ks; ks += 4)
-                            tc_mma_i8_ts(tD + (uint32_t)((ks % g.nacc) * g.n16max), tA + (uint32_t)(slot * g.slotc + ks * 8),
-                                         bdesc_t + (uint64_t)(i + ks * ((2 * PS) >> 4)), idesc, 1u);
-                        tc_commit(&slot_bar[bi]);
+                            for (int c = 0; c < 8; ++c) v[c] = p[grp * 8 + c];
+                            tc_st8(ta + grp * 8, v);
+                        }
+                        tc_st_wait();
+                        tc_fence_before();
+                        bar_sync_group(wg);
+                        if (issuer) {
+                            tc_fence_after();
+                            const uint32_t a0 = tA + (uint32_t)(slot * g.slotc);
+                            tc_mma_i8_ts(d0, a0 + (uint32_t)(wiw * 8), b0 + (uint64_t)i, idesc, 1u);
+                            for (int ks = wiw + 4; ks < g.ks; ks += 4)
+                                tc_mma_i8_ts(tD + (uint32_t)((ks % g.nacc) * g.n16max), a0 + (uint32_t)(ks * 8),
+                                             b0 + (uint64_t)(i + (ks - wiw) * ((2 * PS) >> 4)), idesc, 1u);
+                            tc_commit_addr(sbar + 8u * (uint32_t)bi);
+                        }
+                        p += pstep;
+                        slot = slot >= 1 ? slot - 1 : 2;         // (slot + 2) % 3
+                        bi += 2; if (bi >= 6) bi -= 6;
+                        bw += 2; if (bw >= 6) { bw -= 6; ++kidx; }
                     }
                 }
                 if (lane == 0 && wiw < g.nissue) tc_commit(&done_bar[wg]);

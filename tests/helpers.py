@@ -6,11 +6,14 @@ Contract (BASELINE.json north_star / SURVEY 8d):
   * MCC r and Hessian h within 1e-4 absolute;
   * identical NaN pattern.
 
-Against the cv2-based reference the Hessian tolerance is 1e-4 * max(1, |h|/10): h is
-(hes - median) / std with |h| ~ 10-20 at a good peak, and cv2's float32 correlation noise
-(+-2e-6 in r, see below) comes out of that normalisation as ~5e-6 * |h| (measured on every
-golden variant), i.e. above 1e-4 absolute only where |h| > 10.  Against the exact CPU
-oracle the GPU values are compared far tighter (tests/test_gpu_parity.py).
+KNOWN DEVIATION, REPORTED NOT HIDDEN: against the cv2-based reference the Hessian h misses the 1e-4 ABSOLUTE
+bound on a small fraction of points: measured on the golden set 3 of 563 points (0.5 %), max |dh| = 1.62e-4
+(variant s51_b60, |h| up to 21.6).  Cause: h = (hes - median) / std with |h| ~ 10-20 at a good peak, and cv2's
+float32 DFT noise (+-2e-6 in r) comes out of that normalisation as ~5e-6 * |h|; the exact-integer GPU/oracle side is
+the more accurate one.  ``classify`` therefore returns BOTH the strict figures (``max_dh_abs``, ``n_dh_gt_1e4``) and
+the |h|-scaled one (``max_dh``); ``assert_parity`` bounds the strict ones explicitly (H_ABS_CEIL, H_ABS_FRAC) and
+bench.py prints them in its ``parity`` block.  Against the exact CPU oracle the GPU values are compared far
+tighter (tests/test_gpu_parity.py).
 
 A *tie* exists because cv2.matchTemplate computes the correlation in float32
 (DFT / IPP), off by ~1e-6 from the exact value, whereas the oracle's and the GPU's
@@ -21,6 +24,8 @@ import numpy as np
 
 R_TOL = 1e-4
 H_TOL = 1e-4
+H_ABS_CEIL = 5e-4        # no point may differ from the reference by more than this in h (absolute)
+H_ABS_FRAC = 0.02        # at most this fraction of points may exceed 1e-4 absolute in h
 TIE_EPS = 4e-6
 
 
@@ -53,9 +58,12 @@ def classify(got, ref, exact_value_at=None):
                 continue
         unexplained.append(int(i))
     dr = np.abs(got[same, 3] - ref[same, 3])
-    dh = np.abs(got[same, 4] - ref[same, 4]) / np.maximum(1.0, np.abs(ref[same, 4]) / 10.0)
+    dh_abs = np.abs(got[same, 4] - ref[same, 4])
+    dh = dh_abs / np.maximum(1.0, np.abs(ref[same, 4]) / 10.0)
     return dict(n=len(ref), nan_equal=nan_equal, exact=int(same.sum()), ties=ties, unexplained=unexplained,
-                max_dr=float(dr.max()) if dr.size else 0.0, max_dh=float(dh.max()) if dh.size else 0.0)
+                max_dr=float(dr.max()) if dr.size else 0.0, max_dh=float(dh.max()) if dh.size else 0.0,
+                max_dh_abs=float(dh_abs.max()) if dh_abs.size else 0.0, n_dh_gt_1e4=int((dh_abs > 1e-4).sum()),
+                n_compared=int(same.sum()))
 
 
 def make_exact_lookup(co, pts, img1, img2, img_size, alpha0, angles, opts):
@@ -82,3 +90,6 @@ def assert_parity(stats, r_tol=R_TOL, h_tol=H_TOL):
     assert not stats["unexplained"], "unexplained position/angle mismatches: %r" % (stats,)
     assert stats["max_dr"] <= r_tol, stats
     assert stats["max_dh"] <= h_tol, stats
+    # the strict (absolute) figures, bounded explicitly -- see the module docstring
+    assert stats["max_dh_abs"] <= H_ABS_CEIL, stats
+    assert stats["n_dh_gt_1e4"] <= max(3, int(H_ABS_FRAC * stats["n_compared"])), stats
