@@ -13,13 +13,18 @@ One step = one pass of the hot path over the whole PM grid of one image pair.
             the device -> host read of the result table are inside the timed region.
   roofline: algorithmic FLOPs (sum over points and angles of 2 s^2 R^2) per launch
             over the kernel's average duration, against the measured dense tensor peak of
-            MEASURED_PEAKS.json (the multiply-adds run as u8 IMMA); roofline_fma repeats it against
-            the FP32-FMA peak that BASELINE.json's metric names.
-  cpu_baseline / --impl reference: the NumPy/cv2/scipy port of the reference loop
-            (oracle/pm_oracle.py, same third-party calls as the reference, fork Pool over all
-            host cores) on a bounded sample of the same workload.
-Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank matches the full grid of its
-own image pair (the time-series case, BASELINE configs[4]); no data-path collective.
+            MEASURED_PEAKS.json (the multiply-adds run as tcgen05 kind::i8 MMAs); roofline_fma repeats it
+            against the FP32-FMA peak that BASELINE.json's metric names.
+  configs : the other single-GPU BASELINE configurations (cfg1, cfg3, cfg4) at full size, device-resident.
+  cpu_baseline / --impl reference: the UNMODIFIED reference's own per-point loop (pmlib.use_mcc_mp through a
+            fork Pool over all host cores, from the oracle/_ref copy placed by oracle/build_ref.py; kind
+            "reference") on a bounded sample of the same workload -- the NumPy/cv2/scipy port
+            (oracle/pm_oracle.py, kind "port") only where that copy is absent.
+  parity  : the GPU table against the exact CPU oracle AND against the reference on seeded samples.
+Multi-GPU (torchrun, one rank per GPU): `value` / `e2e` are weak scaling -- every rank matches the full grid of
+its own image pair (the time-series case, BASELINE configs[4]); no data-path collective.  The `strong` block is
+north_star's split of ONE pair: every rank uploads 1/N of the rows, an in-place NCCL all-gather over NVLink
+completes the pair on every GPU, the points are dealt over the ranks and one all-gather returns the table.
 """
 import argparse
 import json
@@ -50,6 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=20000, help="points timed for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=4000, help="points per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1 / cfg3 / cfg4 block")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block at N > 1")
     return ap.parse_args()
 
 
@@ -111,20 +118,32 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_kind():
+    """"reference": the unmodified reference (oracle/_ref copy or /root/reference) can be loaded; else "port"."""
+    from oracle import ref_runner
+    return "reference" if ref_runner.available() else "port"
+
+
 def cpu_port_rate(pts, img1, img2, img_size, angles, sample, threads, seed=0):
-    """vectors/s of the reference-equivalent CPU loop on `sample` points of the workload."""
-    from oracle import pm_oracle
+    """vectors/s of the reference's CPU loop on `sample` points of the workload: the reference's own use_mcc_mp
+    when the reference copy is present, else the port that calls the same third-party routines."""
     n = len(pts[0])
     sel = np.sort(np.random.default_rng(seed).choice(n, min(sample, n), replace=False))
     sub = [p[sel] for p in pts]
-    t0 = time.perf_counter()
-    rows = pm_oracle.run_points(*sub, img1, img2, img_size, 0.0, threads=threads, angles=angles)
+    if cpu_kind() == "reference":
+        from oracle import ref_runner
+        t0 = time.perf_counter()
+        rows = ref_runner.run_reference_points(*sub, img1, img2, img_size, 0.0, threads=threads, angles=angles)
+    else:
+        from oracle import pm_oracle
+        t0 = time.perf_counter()
+        rows = pm_oracle.run_points(*sub, img1, img2, img_size, 0.0, threads=threads, angles=angles)
     dt = time.perf_counter() - t0
     return len(sel) / dt, len(sel), dt, rows, sel
 
 
 def main_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (port, see module doc)."""
+    """--impl reference: the reference's own CPU implementation of the path (see module doc)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -147,11 +166,55 @@ def main_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_description(args.workload, cfg, len(c1))},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": cpu_kind(), "sample": sample,
+                             "source": "oracle/_ref: unmodified sea_ice_drift/pmlib.py use_mcc_mp through a fork Pool"
+                                       if cpu_kind() == "reference" else "oracle/pm_oracle.py (port)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
+
+
+def time_resident(ctx, torch, stream, dev, pts, s, angles, steps, warmup):
+    """Device-timed steps of the hot path on the resident pair; returns (ms per step, dominant-kernel ms, table, status)."""
+    n = len(pts[0])
+    d_pts = torch.from_numpy(np.stack(pts)).to(dev)
+    d_out = torch.empty((n, 5), dtype=torch.float64, device=dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    ptrs = [d_pts[k].data_ptr() for k in range(5)]
+    max_border = int(np.max(pts[4]))
+
+    def step():
+        ctx.run_device(n, *ptrs, max_border, s, angles, 0.0, d_out.data_ptr(), d_status.data_ptr())
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    k = []
+    for _ in range(3):
+        step()
+        k.append(ctx.last_kernel_ms)
+    return ms, float(np.mean(k)), d_out.cpu().numpy(), d_status.cpu().numpy()
+
+
+def reference_parity(out_rows, ref_rows, pts, img1, img2, s, angles):
+    """GPU rows against the reference's rows on the same points: exact / tie-explained / unexplained, max |dr|,
+    max |dh| and the number of points above north_star's 1e-4 absolute bound in h (tests/helpers.py explains it)."""
+    from oracle import c_oracle
+    from tests.helpers import classify, make_exact_lookup
+    opts = dict(rot_order=0, hes_norm=True, hes_smth=False, mcc_norm=False)
+    st = classify(out_rows, ref_rows, make_exact_lookup(c_oracle, pts, img1, img2, s, 0.0, angles, opts))
+    return {"points": st["n"], "nan_pattern_equal": bool(st["nan_equal"]), "position_angle_exact": st["exact"],
+            "tie_explained": st["ties"], "unexplained": len(st["unexplained"]), "max_abs_dr": st["max_dr"],
+            "max_abs_dh": st["max_dh_abs"], "n_dh_above_1e-4": st["n_dh_gt_1e4"],
+            "note": "h above 1e-4 absolute only where |h| > 10: cv2's float32 DFT noise (2e-6 in r) amplified by "
+                    "(hes - median) / std; the exact-integer GPU side is the more accurate one"}
 
 
 def main_ours(args):
@@ -270,6 +333,75 @@ def main_ours(args):
     h2d = int(img1.nbytes + img2.nbytes + n * 5 * 8 + n * 4 + len(angles) * 5 * 8)
     d2h = int(n * 5 * 8)
     same_as_resident = bool(np.array_equal(host_out, out, equal_nan=True))
+    # the same call with plain (pageable) NumPy images -- what the Python drop-in passes: staged upload inside the library
+    for _ in range(1):
+        ctx.run_pair(img1, img2, c1, r1, c2, r2, b, s, angles, 0.0)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pg_steps = max(2, min(e2e_steps, 5))
+    for _ in range(pg_steps):
+        ctx.run_pair(img1, img2, c1, r1, c2, r2, b, s, angles, 0.0)
+    dt_pg = max_over_ranks(time.perf_counter() - t0)
+    e2e_pageable = {"value": total_points * pg_steps / dt_pg, "unit": UNIT, "ms_per_step": 1e3 * dt_pg / pg_steps,
+                    "steps": pg_steps, "call": "sid_run_pair with pageable NumPy images (staged through a pinned double buffer)"}
+
+    # ---- north_star's split of ONE pair over the ranks (strong scaling): slab upload + NVLink all-gather + one result all-gather
+    strong = None
+    if world > 1 and not args.no_strong:
+        from sea_ice_drift_b200 import sharding
+        si1, si2, sc1, sr1, sc2, sr2, sb, _ = syn.make_config(args.workload, seed=0, side=args.side or None, grid=args.grid or None)
+        si1 = torch.from_numpy(si1).pin_memory().numpy()
+        si2 = torch.from_numpy(si2).pin_memory().numpy()
+        table = None
+        for _ in range(2):
+            table = sharding.use_mcc_batch_split(sc1, sr1, sc2, sr2, sb, si1, si2, s, 0.0, angles=angles, device=local_rank)
+        barrier(); torch.cuda.synchronize()
+        st_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(st_steps):
+            table = sharding.use_mcc_batch_split(sc1, sr1, sc2, sr2, sb, si1, si2, s, 0.0, angles=angles, device=local_rank)
+        dt_st = max_over_ranks(time.perf_counter() - t0)
+        plan = sharding.SplitPlan(si1.shape[0], si1.shape[1], world)
+        strong = {"scaling": "strong", "value": len(sc1) * st_steps / dt_st, "unit": UNIT, "ms_per_pair": 1e3 * dt_st / st_steps,
+                  "steps": st_steps, "points": int(len(sc1)),
+                  "h2d_bytes_per_rank": int(2 * plan.rows_per * plan.cols), "nvlink_allgather_bytes_per_rank": int(2 * plan.gather_bytes),
+                  "result_allgather_bytes": int(-(-len(sc1) // world) * world * 40),
+                  "collectives_per_step": "2 in-place all_gather_into_tensor of the image row slabs (NCCL over NVLink) + 1 of the result rows",
+                  "table_checksum": float(np.nansum(table[:, :2]))}
+        if rank == 0 and world == int(os.environ.get("WORLD_SIZE", "1")):
+            # the sharded table must equal this rank's own single-GPU table of the same pair
+            ctx.set_pair(si1, si2)
+            one = ctx.run(sc1, sr1, sc2, sr2, sb, s, angles, 0.0)
+            strong["equals_single_gpu_table"] = bool(np.array_equal(table, one, equal_nan=True))
+            ctx.set_pair(img1p, img2p)
+        barrier()
+
+    # ---- the other single-GPU BASELINE configurations at full size (device-resident)
+    configs = None
+    if world == 1 and not args.no_configs and args.workload == "cfg2":
+        configs = {}
+        ctx.set_stream(stream.cuda_stream)
+        for name, steps_c in (("cfg3", 10), ("cfg4", 4), ("cfg1", 20)):
+            cc = dict(syn.CONFIGS[name])
+            if args.side:
+                cc["side"] = args.side if name != "cfg1" else min(args.side, cc["side"])
+            if args.grid:
+                cc["grid"] = args.grid
+            if name == "cfg1":
+                i1, i2, q1, q2, q3, q4, q5, cc2 = syn.make_config("cfg1", seed=0, side=cc["side"], grid=cc["grid"])
+                ctx.set_pair(i1, i2)
+                cpts = [q1, q2, q3, q4, q5]
+            else:       # cfg3 / cfg4 use the EW pair that is already resident (same seed, same warp)
+                m = syn.rotation_matrix(img1.shape, cc["warp"][1])
+                cpts = list(syn.hot_loop_inputs(img1, m, cc["grid"], cc["img_size"], cc["border"], rank))
+            ms_c, k_ms, o_c, st_c = time_resident(ctx, torch, stream, dev, cpts, cc["img_size"], cc["angles"], steps_c, 3)
+            fl = float(flops_per_point(cc["img_size"], cpts[4][st_c == 1], len(cc["angles"])).sum())
+            configs[name] = {"workload": workload_description(name, cc, len(cpts[0])), "points": int(len(cpts[0])),
+                             "valid": int((st_c == 1).sum()), "value": len(cpts[0]) / (ms_c * 1e-3), "unit": UNIT,
+                             "ms_per_step": ms_c, "kernel_ms": k_ms, "steps": steps_c,
+                             "tflops_equiv": fl / (k_ms * 1e-3) / 1e12}
+        ctx.set_stream(None)
+        ctx.set_pair(img1p, img2p)
 
     line = None
     if rank == 0:
@@ -287,9 +419,14 @@ def main_ours(args):
         if cpu_run is not None:
             threads, rate, m, dt, rows, csel = cpu_run
             agree = int((np.nan_to_num(rows[:, :3], nan=-1) == np.nan_to_num(out[csel][:, :3], nan=-1)).all(axis=1).sum())
-            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "other_thread_counts": cpu_extra,
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": cpu_kind(), "other_thread_counts": cpu_extra,
+                   "source": "oracle/_ref: unmodified sea_ice_drift/pmlib.py use_mcc_mp through a fork Pool"
+                             if cpu_kind() == "reference" else "oracle/pm_oracle.py (port)",
                    "sample": "%d seeded random grid points of the same workload in %.1f s (fork Pool, %d workers); "
                              "%d/%d rows agree with the GPU in position and angle" % (m, dt, threads, agree, m)}
+            if cpu_kind() == "reference":
+                parity["vs_reference"] = reference_parity(out[csel], rows, [x[csel] for x in (c1, r1, c2, r2, b)],
+                                                          img1, img2, s, angles)
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
         peaks = {}
         try:
@@ -306,23 +443,29 @@ def main_ours(args):
             pass
         tensor_peak = float(peaks.get("bf16_tflops") or 1590.0)
         imma_peak = sm_count * 1950 * 2 * sm_max * 1e6 / 1e12
+        i8_peak = sm_count * 7949 * 2 * sm_max * 1e6 / 1e12       # tcgen05 kind::i8 measured: profiles/r02_tcgen05_i8_rates.txt
+        if configs:
+            for cdict in configs.values():
+                cdict["roofline_frac"] = cdict["tflops_equiv"] / tensor_peak
+                cdict["frac_of_fp32_fma_peak"] = cdict["tflops_equiv"] / peak_tflops
         # main object: the correlation of the dominant kernel runs on the tensor pipe (exact u8 x u8 -> s32 IMMA), so the
         # bounding roofline is "tensor" against the measured dense bf16 peak of MEASURED_PEAKS.json
         roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                     "frac": achieved / tensor_peak, "traffic": traffic,
-                    "kernel": "sid::pm_points_kernel", "kernel_ms": kernel_ms, "step_ms": ms_per_step,
-                    "kernels_per_step": "pm_points_kernel (correlation, dominant) + pm_tail_kernel (peak statistics)",
+                    "kernel": "sid::pm_tc_kernel", "kernel_ms": kernel_ms, "step_ms": ms_per_step,
+                    "kernels_per_step": "pm_tc_kernel (tcgen05 correlation, dominant) + pm_tail_kernel (peak statistics)",
                     "algorithmic_flops_per_launch": flops_step,
                     "peak_source": ("bf16_tflops of MEASURED_PEAKS.json (of measured)" if peaks.get("bf16_tflops")
                                     else "1.59 PFLOP/s (of fallback)"),
+                    "u8_tcgen05_peak": i8_peak, "frac_of_u8_tcgen05_peak": achieved / i8_peak,
                     "u8_mma_sync_peak": imma_peak, "frac_of_u8_mma_sync_peak": achieved / imma_peak,
                     "frac_of_fp32_fma_peak": achieved / peak_tflops,
                     "note": "algorithmic FLOPs = sum over points and angles of 2 s^2 R^2 (SURVEY 8d), multiply-adds of the direct-form "
-                            "correlation only; they run as mma.sync.m16n8k32 u8 IMMA (measured 1950 MAC/clk/SM = u8_mma_sync_peak, "
-                            "profiles/r01_pipe_rates_b200.txt). ncu: tensor pipe ~22-28 % active, issue slots 47 %, shared-memory pipe "
-                            "70 %: the kernel is bound by instruction issue and shared memory in its non-MAC phases (window sums, template "
-                            "gather, FP64 normalisation), not by the tensor pipe (profiles/README.md). BASELINE.json's own figure, the "
-                            "fraction of the FP32-FMA roofline, is in roofline_fma",
+                            "correlation only; they run as tcgen05.mma kind::i8 (u8 x u8 -> s32, TMEM accumulators; measured pipe rate "
+                            "7949 MAC/clk/SM = u8_tcgen05_peak, profiles/r02_tcgen05_i8_rates.txt). The Toeplitz formulation issues "
+                            "~3.3x the algorithmic MACs and the tensor pipe is ~10 % busy: the kernel is bound by the latency chains of "
+                            "its non-MAC phases (template gather, FP64 normalisation, window statistics) at 16 resident warps per SM "
+                            "(profiles/README.md). BASELINE.json's own figure, the fraction of the FP32-FMA roofline, is in roofline_fma",
                     "hbm_gbs_measured_peak": peaks.get("hbm_gbs")}
         roofline_fma = {"bound": "fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                         "frac": achieved / peak_tflops, "traffic": traffic,
@@ -344,7 +487,9 @@ def main_ours(args):
                         "steps": e2e_steps, "ms_per_step": 1e3 * dt_e2e / e2e_steps,
                         "call": "sid_run_pair: pinned host image pair + host point arrays in, host result table out; "
                                 "upload in row bands overlapped with the fused kernel"},
-                "roofline": roofline, "roofline_fma": roofline_fma, "cpu_baseline": cpu, "parity": parity}
+                "e2e_pageable": e2e_pageable,
+                "roofline": roofline, "roofline_fma": roofline_fma, "cpu_baseline": cpu, "parity": parity,
+                "configs": configs, "strong": strong}
     ctx.close()
     if world > 1:
         dist.barrier()

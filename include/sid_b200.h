@@ -84,6 +84,17 @@ int sid_set_pair_device(sid_ctx *ctx,
                         const uint8_t *d_img1, int rows1, int cols1, int64_t pitch1,
                         const uint8_t *d_img2, int rows2, int cols2, int64_t pitch2);
 
+/* Layout the library uses for a resident image: row pitch (a legal TMA stride: multiple of 16, >= cols + 16) and the
+ * total allocation (pitch * rows + tail slack).  For callers that fill the pair themselves (sid_adopt_pair_device). */
+int sid_pair_layout(int rows, int cols, int64_t *pitch, int64_t *bytes);
+/* Use CALLER-OWNED device buffers as the resident pair, without a copy: the multi-GPU path, where every rank
+ * uploads one row slab of each image and an in-place NCCL all-gather over NVLink completes the buffers (replaces
+ * the fork/copy-on-write replication of the reference's Pool, pmlib.py:430-448).  The buffers must follow
+ * sid_pair_layout (256-byte aligned base, pitch, bytes) and outlive their use; the library never frees them. */
+int sid_adopt_pair_device(sid_ctx *ctx,
+                          uint8_t *d_img1, int rows1, int cols1, int64_t pitch1, int64_t bytes1,
+                          uint8_t *d_img2, int rows2, int cols2, int64_t pitch2, int64_t bytes2);
+
 /* use_mcc for n grid points (host arrays in, host array out, synchronous).
  *   c1, r1        float pixel coordinates on image 1
  *   c2fg, r2fg    integer-valued first guess on image 2

@@ -57,9 +57,10 @@ def find(s):
 
 
 marks = [("helpers/ptx wrappers", 1), ("setup + point fetch", find("pm_tc_kernel(const PmArgs a")), ("1 stage window", find("---- 1. stage the window")),
-         ("2a horizontal sums", find("---- 2a.")), ("2b vertical sums + den", find("---- 2b.")),
+         ("2 mma sums: squares LUT pass", find("---- 2 (tensor cores)")), ("2 mma sums: tiles (clear/gen/mma)", find("const int ntile_s =")),
+         ("2 mma sums: sliding + den", find("// vertical sliding sums along the lane")), ("2 legacy sums", find("---- 2a.")),
          ("3 batch setup + gather", find("---- 3. angle batches")), ("mac: tile setup + clears", find("---- correlation on the tensor cores")),
-         ("mac: row loop (gen+issue)", find("for (int i = wg; i < s; i += 2)")), ("mac: commit/done wait", find("tc_commit(&done_bar[wg]);")),
+         ("mac: row loop (gen+issue)", find("// Row loop.")), ("mac: commit/done wait", find("if (lane == 0 && wiw < g.nissue) tc_commit(&done_bar[wg]);")),
          ("epilogue (ld + normalise)", find("// epilogue: each warp group")), ("argmax merge / best angle", find("for (int a2 = 0; a2 < nb; ++a2)")),
          ("4 tail hand-off", find("---- 4. peak statistics")), ("end", 10 ** 9)]
 marks = [m for m in marks if m[1] is not None]

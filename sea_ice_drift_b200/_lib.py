@@ -22,7 +22,7 @@ SID_HES_NORM, SID_HES_SMTH, SID_MCC_NORM = 1, 2, 4
 
 EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
-    "sid_set_pair", "sid_set_pair_device", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
+    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
     "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian", "sid_knn_hamming2",
     "sid_deformation",
 ]
@@ -60,6 +60,9 @@ def load_library():
         pair = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int64]
         lib.sid_set_pair.argtypes = pair
         lib.sid_set_pair_device.argtypes = pair
+        lib.sid_pair_layout.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.sid_adopt_pair_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                              C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64]
         lib.sid_run.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
         lib.sid_run_pair.argtypes = pair + [C.c_int64] + [C.c_void_p] * 5 + \
@@ -104,6 +107,15 @@ def angle_table(angles, alpha0, img_size):
         shift = centre.dot(rot)
         tab[k] = (rot[0, 0], rot[1, 0], shift[0], shift[1])
     return tab
+
+
+def pair_layout(rows, cols):
+    """(pitch, bytes) of a resident image of ``rows x cols`` in the library's layout (sid_pair_layout)."""
+    pitch, nbytes = C.c_int64(), C.c_int64()
+    rc = load_library().sid_pair_layout(int(rows), int(cols), C.byref(pitch), C.byref(nbytes))
+    if rc:
+        raise ValueError("sid_pair_layout(%r, %r) failed" % (rows, cols))
+    return int(pitch.value), int(nbytes.value)
 
 
 def flags_from_kwargs(hes_norm=True, hes_smth=False, mcc_norm=False):
@@ -179,6 +191,14 @@ class Context(object):
     def set_pair_device(self, ptr1, shape1, pitch1, ptr2, shape2, pitch2):
         self._check(self._lib.sid_set_pair_device(
             self._h, C.c_void_p(ptr1), shape1[0], shape1[1], pitch1, C.c_void_p(ptr2), shape2[0], shape2[1], pitch2))
+        self._pair_key = None
+        return self
+
+    def adopt_pair_device(self, ptr1, shape1, pitch1, bytes1, ptr2, shape2, pitch2, bytes2):
+        """Use caller-owned device buffers (layout of :func:`pair_layout`) as the resident pair, no copy."""
+        self._check(self._lib.sid_adopt_pair_device(
+            self._h, C.c_void_p(ptr1), shape1[0], shape1[1], pitch1, bytes1,
+            C.c_void_p(ptr2), shape2[0], shape2[1], pitch2, bytes2))
         self._pair_key = None
         return self
 

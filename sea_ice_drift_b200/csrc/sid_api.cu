@@ -29,6 +29,7 @@ constexpr size_t IMG_TAIL_SLACK = 4096;   // bytes readable past the last image 
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool owned = true;      // false: caller-owned memory adopted by sid_adopt_pair_device (never freed / grown here)
 };
 
 }  // namespace
@@ -95,11 +96,12 @@ int allow_max_smem(sid_ctx *ctx, const void *kernel) {
 }
 
 int reserve(sid_ctx *ctx, DevBuf &b, size_t bytes) {
-    if (bytes <= b.cap) return SID_OK;
-    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    if (bytes <= b.cap && b.owned) return SID_OK;
+    if (b.p && b.owned) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0; b.owned = true;
     size_t want = bytes + bytes / 4 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SID_ENOMEM, "device allocation failed"); }
+    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(ctx, SID_ENOMEM, "device allocation failed"); }
     b.cap = want;
     return SID_OK;
 }
@@ -120,7 +122,7 @@ int upload_image(sid_ctx *ctx, DevBuf &buf, long long &pitch, const uint8_t *src
     if (!src || rows <= 0 || cols <= 0 || src_pitch < cols) return fail(ctx, SID_EINVAL, "bad image arguments");
     pitch = padded_pitch(cols);
     const size_t bytes = (size_t)pitch * rows + IMG_TAIL_SLACK;
-    const bool fresh = bytes > buf.cap;
+    const bool fresh = bytes > buf.cap || !buf.owned;
     int rc = reserve(ctx, buf, bytes);
     if (rc) return rc;
     if (fresh) CU(cudaMemsetAsync(buf.p, 0, buf.cap, ctx->stream));
@@ -336,8 +338,8 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         return fail(ctx, SID_ECUDA, msg);
     }
     if (getenv("SID_DEBUG"))
-        fprintf(stderr, "[sid] launch: tc=%d kidx=%d threads=%d smem=%zu occ(api)=%d tmem_cols=%d nab=%d ks=%d nacc=%d nb8=%d slotc=%d n16max=%d wrows=%d npanels=%d\n",
-                (int)use_tc, kidx, threads, smem, occ, tg.tmem_cols, tg.nab, tg.ks, tg.nacc, tg.nb8, tg.slotc, tg.n16max, tg.wrows, tg.npanels);
+        fprintf(stderr, "[sid] launch: tc=%d kidx=%d threads=%d smem=%zu occ(api)=%d tmem_cols=%d nab=%d ks=%d nacc=%d nb8=%d slotc=%d n16max=%d wrows=%d npanels=%d mma_sums=%d\n",
+                (int)use_tc, kidx, threads, smem, occ, tg.tmem_cols, tg.nab, tg.ks, tg.nacc, tg.nb8, tg.slotc, tg.n16max, tg.wrows, tg.npanels, tg.mma_sums);
     if (use_tc) {
         // The occupancy API answers 1 for a kernel that executes tcgen05.alloc with a run-time column count (it has to
         // assume all 512 columns); residency is really bounded by registers, shared memory and the columns we ask for.
@@ -429,7 +431,7 @@ void sid_destroy(sid_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->img1, &ctx->img2, &ctx->pts, &ctx->order, &ctx->out, &ctx->status,
                       &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs};
-    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : bufs) if (b->p && b->owned) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     for (cudaEvent_t e : ctx->stage_event) if (e) cudaEventDestroy(e);
@@ -492,6 +494,35 @@ int sid_set_pair(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_
 int sid_set_pair_device(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1, int64_t pitch1,
                         const uint8_t *img2, int rows2, int cols2, int64_t pitch2) {
     return set_pair_impl(ctx, img1, rows1, cols1, pitch1, img2, rows2, cols2, pitch2, cudaMemcpyDeviceToDevice);
+}
+
+int sid_pair_layout(int rows, int cols, int64_t *pitch, int64_t *bytes) {
+    if (rows <= 0 || cols <= 0 || !pitch || !bytes) return SID_EINVAL;
+    *pitch = padded_pitch(cols);
+    *bytes = *pitch * (int64_t)rows + (int64_t)IMG_TAIL_SLACK;
+    return SID_OK;
+}
+
+int sid_adopt_pair_device(sid_ctx *ctx, uint8_t *d_img1, int rows1, int cols1, int64_t pitch1, int64_t bytes1,
+                          uint8_t *d_img2, int rows2, int cols2, int64_t pitch2, int64_t bytes2) {
+    if (!ctx) return SID_EINVAL;
+    if (!d_img1 || !d_img2 || rows1 <= 0 || cols1 <= 0 || rows2 <= 0 || cols2 <= 0)
+        return fail(ctx, SID_EINVAL, "bad image arguments");
+    if (pitch1 < padded_pitch(cols1) || pitch2 < padded_pitch(cols2) || (pitch1 & 15) || (pitch2 & 15) ||
+        ((uintptr_t)d_img1 & 255) || ((uintptr_t)d_img2 & 255))
+        return fail(ctx, SID_EINVAL, "adopted images need the layout of sid_pair_layout (pitch, 256-byte aligned base)");
+    if (bytes1 < pitch1 * (int64_t)rows1 + (int64_t)IMG_TAIL_SLACK || bytes2 < pitch2 * (int64_t)rows2 + (int64_t)IMG_TAIL_SLACK)
+        return fail(ctx, SID_EINVAL, "adopted images need the tail slack of sid_pair_layout");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));                    // nothing in flight still reads the old pair
+    DevBuf *bufs[2] = {&ctx->img1, &ctx->img2};
+    for (DevBuf *b : bufs) { if (b->p && b->owned) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    ctx->img1.p = d_img1; ctx->img1.cap = (size_t)bytes1; ctx->img1.owned = false;
+    ctx->img2.p = d_img2; ctx->img2.cap = (size_t)bytes2; ctx->img2.owned = false;
+    ctx->rows1 = rows1; ctx->cols1 = cols1; ctx->pitch1 = pitch1;
+    ctx->rows2 = rows2; ctx->cols2 = cols2; ctx->pitch2 = pitch2;
+    ctx->have_pair = true;
+    return SID_OK;
 }
 
 static int upload_angles(sid_ctx *ctx, int n_angles, const double *angles, const double *angle_tab,
@@ -643,7 +674,7 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
         ctx->pitch1 = padded_pitch(pair->cols1);
         ctx->pitch2 = padded_pitch(pair->cols2);
         const size_t b1 = (size_t)ctx->pitch1 * pair->rows1 + IMG_TAIL_SLACK, b2 = (size_t)ctx->pitch2 * pair->rows2 + IMG_TAIL_SLACK;
-        const bool fresh1 = b1 > ctx->img1.cap, fresh2 = b2 > ctx->img2.cap;
+        const bool fresh1 = b1 > ctx->img1.cap || !ctx->img1.owned, fresh2 = b2 > ctx->img2.cap || !ctx->img2.owned;
         if ((rc = reserve(ctx, ctx->img1, b1))) return rc;
         if ((rc = reserve(ctx, ctx->img2, b2))) return rc;
         // the copy stream must not overwrite images an earlier launch on the compute stream still reads

@@ -75,6 +75,120 @@ def use_mcc_batch_sharded(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alph
     return gather_rows(local, idx, n, dist, _collective_device(dist, kwargs.get('device')))
 
 
+# ---------------------------------------------------------------------------------------------------------
+# north_star's multi-GPU data plane for ONE pair: every rank uploads one row slab of each image, an in-place
+# all-gather over NVLink completes the padded image buffers on every GPU (replaces the fork / copy-on-write
+# replication of the reference's Pool, pmlib.py:430-448), the points are dealt by search radius, the kernel writes
+# its rows straight into its slab of a result buffer, and ONE all-gather assembles the table.
+
+class SplitPlan(object):
+    """Row slabs of an image of ``rows`` lines over ``world`` ranks (equal slabs, the last one padded)."""
+
+    def __init__(self, rows, cols, world):
+        from . import _lib
+        self.rows, self.cols, self.world = int(rows), int(cols), int(world)
+        self.pitch, self.bytes = _lib.pair_layout(rows, cols)
+        self.rows_per = -(-self.rows // self.world)
+        self.slab = self.rows_per * self.pitch                       # bytes every rank contributes
+        self.gather_bytes = self.slab * self.world                   # >= rows * pitch
+        self.alloc_bytes = max(self.bytes, self.gather_bytes) + 256  # tail slack of the layout included
+
+    def row_range(self, rank):
+        r0 = min(self.rows, rank * self.rows_per)
+        return r0, min(self.rows, r0 + self.rows_per)
+
+
+_split_buffers = {}
+
+
+def _split_buffer(key, plan, device):
+    """Cached zero-initialised device buffer (torch uint8, 256-byte aligned by the allocator)."""
+    import torch
+    buf = _split_buffers.get(key)
+    if buf is None or buf.numel() < plan.alloc_bytes or buf.device != device:
+        buf = torch.zeros(plan.alloc_bytes, dtype=torch.uint8, device=device)
+        _split_buffers[key] = buf
+    return buf
+
+
+def replicate_pair(img1, img2, dist, ctx=None, device=None):
+    """Make ``img1`` / ``img2`` resident on EVERY rank's GPU while each rank transfers only 1/world of them over
+    PCIe: rank r copies rows ``SplitPlan.row_range(r)`` of both images host -> device into its slab of the padded
+    buffers, then one in-place ``all_gather_into_tensor`` per image fills the rest over NVLink.  The context adopts
+    the buffers without a copy (``sid_adopt_pair_device``).  Returns the bytes this rank uploaded."""
+    import torch
+    from . import _lib
+    ctx = ctx or _lib.default_context(device)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nccl = dist.get_backend() == 'nccl'
+    dev = torch.device('cuda', ctx.device) if nccl else torch.device('cpu')
+    uploaded = 0
+    bufs = []
+    for k, img in enumerate((img1, img2)):
+        img = _lib.as_u8_image(img)
+        plan = SplitPlan(img.shape[0], img.shape[1], world)
+        buf = _split_buffer((ctx.device if nccl else 'cpu', k), plan, dev)
+        r0, r1 = plan.row_range(rank)
+        mine = buf[rank * plan.slab:(rank + 1) * plan.slab]
+        if r1 > r0:
+            src = torch.from_numpy(img[r0:r1])
+            mine.view(plan.rows_per, plan.pitch)[:r1 - r0, :plan.cols].copy_(src, non_blocking=True)
+            uploaded += (r1 - r0) * plan.cols
+        whole = buf[:plan.gather_bytes]
+        # in place: NCCL's all-gather is in place when the send buffer is the rank's own slot of the receive buffer
+        dist.all_gather_into_tensor(whole, mine if nccl else mine.clone())
+        bufs.append((buf, plan))
+    if nccl:
+        torch.cuda.current_stream(dev).synchronize()
+        (b1, p1), (b2, p2) = bufs
+        ctx.adopt_pair_device(b1.data_ptr(), (p1.rows, p1.cols), p1.pitch, b1.numel(),
+                              b2.data_ptr(), (p2.rows, p2.cols), p2.pitch, b2.numel())
+    return uploaded, bufs
+
+
+def use_mcc_batch_split(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, **kwargs):
+    """``use_mcc_batch`` for ONE pair over all ranks of the NCCL process group (north_star's split): the pair is
+    replicated by :func:`replicate_pair` (1/world of it per PCIe link + one all-gather over NVLink), the points are
+    dealt by :func:`shard_indices`, every rank's kernel writes its rows into its slab of the result buffer and one
+    ``all_gather_into_tensor`` assembles the (N, 5) table on every rank.  Every rank passes the same arguments.
+    Falls back to :func:`use_mcc_batch_sharded` (each rank uploads the whole pair) without NCCL."""
+    dist = _dist()
+    n = len(c1)
+    if dist is None or dist.get_backend() != 'nccl' or n == 0:
+        return use_mcc_batch_sharded(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, **kwargs)
+    import torch
+    from . import _lib
+    ctx = _lib.default_context(kwargs.get('device'))
+    dev = torch.device('cuda', ctx.device)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    replicate_pair(img1, img2, dist, ctx)
+    border = np.asarray(border, dtype=np.float64)
+    idx = shard_indices(border, world, rank)
+    n_max = -(-n // world)
+    pts = np.zeros((5, n_max), dtype=np.float64)
+    for k, arr in enumerate((c1, r1, c2fg, r2fg, border)):
+        pts[k, :len(idx)] = np.asarray(arr, dtype=np.float64)[idx]
+    pts[:, len(idx):] = np.nan                                    # padding rows: rejected up front, NaN out
+    d_pts = torch.from_numpy(pts).to(dev)
+    table = torch.empty((world, n_max, 5), dtype=torch.float64, device=dev)
+    flags = _lib.flags_from_kwargs(kwargs.get('hes_norm', True), kwargs.get('hes_smth', False), kwargs.get('mcc_norm', False))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    try:
+        ctx.run_device(n_max, *[d_pts[k].data_ptr() for k in range(5)], int(np.nanmax(border)) if n else 1, img_size,
+                       list(kwargs.get('angles', [-3, 0, 3])), alpha0, table[rank].data_ptr(),
+                       rot_order=kwargs.get('rot_order', 0), flags=flags, mtype=kwargs.get('mtype', _lib.SID_TM_CCOEFF_NORMED))
+        dist.all_gather_into_tensor(table.view(world * n_max, 5), table[rank])        # in place, the ONE result collective
+        host = table.cpu().numpy()
+    finally:
+        ctx.set_stream(None)
+    out = np.full((n, 5), np.nan, dtype=np.float64)
+    for r in range(world):
+        ridx = shard_indices(border, world, r)
+        out[ridx] = host[r, :len(ridx)]
+    return out
+
+
 def shard_pairs(n_pairs, world_size, rank):
     """Indices of the image pairs of a time series that rank ``rank`` processes (BASELINE configs[4]: whole
     pairs are dealt round-robin, so no image is replicated and nothing is exchanged during the compute)."""

@@ -85,11 +85,11 @@ def make_exact_lookup(co, pts, img1, img2, img_size, alpha0, angles, opts):
     return lookup
 
 
-def assert_parity(stats, r_tol=R_TOL, h_tol=H_TOL):
+def assert_parity(stats, r_tol=R_TOL, h_tol=H_TOL, h_abs_ceil=H_ABS_CEIL, h_abs_frac=H_ABS_FRAC):
     assert stats["nan_equal"], "NaN pattern differs: %r" % (stats,)
     assert not stats["unexplained"], "unexplained position/angle mismatches: %r" % (stats,)
     assert stats["max_dr"] <= r_tol, stats
     assert stats["max_dh"] <= h_tol, stats
     # the strict (absolute) figures, bounded explicitly -- see the module docstring
-    assert stats["max_dh_abs"] <= H_ABS_CEIL, stats
-    assert stats["n_dh_gt_1e4"] <= max(3, int(H_ABS_FRAC * stats["n_compared"])), stats
+    assert stats["max_dh_abs"] <= h_abs_ceil, stats
+    assert stats["n_dh_gt_1e4"] <= max(3, int(h_abs_frac * stats["n_compared"])), stats

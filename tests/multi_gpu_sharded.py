@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 from sea_ice_drift_b200 import synthetic as syn, pmlib
-from sea_ice_drift_b200.sharding import use_mcc_batch_sharded, use_mcc_series
+from sea_ice_drift_b200.sharding import use_mcc_batch_sharded, use_mcc_batch_split, use_mcc_series
 rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -20,6 +20,14 @@ flag = torch.tensor([1 if same else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("sharded(%d ranks) == single GPU: %s   (%d points, %d NaN)" % (dist.get_world_size(), bool(flag.item()), len(c1), int(np.isnan(single[:, 0]).sum())))
+# north_star's split: slab upload + in-place all-gather of the pair, kernel rows into the gathered result buffer
+split = use_mcc_batch_split(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=cfg["angles"])
+same_split = np.array_equal(split, single, equal_nan=True)
+flag = torch.tensor([1 if same_split else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("split(%d ranks: slab upload + NVLink all-gather) == single GPU: %s" % (dist.get_world_size(), bool(flag.item())))
+same = same and same_split
 # time series: 5 ragged pairs dealt round-robin to the ranks, twice (the second call reuses the staging buffers)
 items = []
 for k in range(5):

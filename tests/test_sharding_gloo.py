@@ -164,3 +164,61 @@ def test_bind_rank_to_gpu_is_a_no_op_without_a_gpu():
     assert cores is None or set(cores) <= before          # never widens the affinity, never raises
     if cores is None:
         assert os.sched_getaffinity(0) == before
+
+
+def _replicate_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from sea_ice_drift_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        img1 = rng.integers(1, 256, (301, 257), dtype=np.uint8)      # odd sizes: the last slab is padded
+        img2 = rng.integers(1, 256, (299, 263), dtype=np.uint8)
+
+        class FakeCtx(object):                                       # no GPU here: only the buffers are checked
+            device = 0
+        uploaded, bufs = sharding.replicate_pair(img1, img2, dist, ctx=FakeCtx())
+        out = []
+        for (buf, plan), img in zip(bufs, (img1, img2)):
+            full = buf[:plan.rows * plan.pitch].numpy().reshape(plan.rows, plan.pitch)
+            out.append((np.array_equal(full[:, :plan.cols], img), int(full[:, plan.cols:].max()), plan.row_range(rank)))
+        q.put((rank, uploaded, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicate_pair_slabs_fill_every_rank():
+    """north_star's replication: each rank contributes 1/world of the rows, the all-gather completes the padded
+    image on every rank (gloo stand-in for the NCCL all-gather over NVLink)."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_replicate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = 0
+    for rank, uploaded, out in got:
+        total += uploaded
+        for same, pad_max, (r0, r1) in out:
+            assert same and pad_max == 0 and r1 > r0
+    assert total == 301 * 257 + 299 * 263                            # every byte crossed "PCIe" exactly once
+
+
+def test_split_plan_geometry():
+    from sea_ice_drift_b200.sharding import SplitPlan
+    for rows, world in ((10400, 8), (301, 2), (7, 8)):
+        plan = SplitPlan(rows, 10400, world)
+        assert plan.pitch % 16 == 0 and plan.pitch >= 10400 + 16
+        ranges = [plan.row_range(r) for r in range(world)]
+        assert ranges[0][0] == 0 and max(r1 for _, r1 in ranges) == rows
+        assert all(a[1] == b[0] or b[0] == rows for a, b in zip(ranges, ranges[1:]))
+        assert plan.gather_bytes == world * plan.slab and plan.alloc_bytes >= plan.bytes
