@@ -581,6 +581,77 @@ __global__ void __launch_bounds__(128) k_rate2(Rate2Args a) {
     __syncthreads();
     if (warp == 0) tmem_dealloc(tb, 512);
 }
+
+// cycle breakdown of one row iteration of the simple (4 gen warps, thread 0 issues) pipeline, thread 0's view
+struct TimingArgs { const uint8_t *win; const uint8_t *tpl; long long *acc; int off; int reps; };
+__global__ void __launch_bounds__(128) k_rowtime(TimingArgs a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ __align__(8) unsigned long long bar[3];
+    __shared__ uint32_t tbase_s;
+    uint8_t *sW = sm;
+    uint8_t *sT = sm + 6 * CWROWS * 16;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 6 * CWROWS * 16 + CNA * CTANG; e += 128) sm[e] = (uint8_t)(e * 13 + 1);
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(&tbase_s, 256);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tbase_s;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t tD = tb, tA = tb + 144;
+    const int m = tid, x = m / 3, ang = m - 3 * x;
+    const int q = x + a.off;
+    const int cw0 = min((((warp * 32) / 3) + a.off) >> 2, 8);
+    const uint32_t *trow = reinterpret_cast<const uint32_t *>(sT + (size_t)ang * CTANG + (q & 3) * CTPITCH) + (CTL >> 2) - (q >> 2) + cw0;
+    const uint32_t idesc = make_idesc_u8(128, 48);
+    unsigned ph[3] = {0, 0, 0};
+    long long t_wait = 0, t_lds = 0, t_st = 0, t_stwait = 0, t_sync = 0, t_issue = 0;
+    for (int rep = 0; rep < a.reps; ++rep) {
+        for (int i = 0; i < CS; ++i) {
+            const int slot = i % 3;
+            long long c0 = clock64();
+            if (i >= 3) { mbar_wait(&bar[slot], ph[slot]); ph[slot] ^= 1u; tc_fence_after(); }
+            long long c1 = clock64();
+            uint32_t v[16];
+            const uint32_t *p = trow + i * (4 * CTPITCH / 4);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = p[c];
+            uint32_t sink = 0;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sink ^= v[c];
+            if (sink == 0x12345u) a.acc[100] = 1;             // force the loads to complete here
+            long long c2 = clock64();
+            tmem_st16(tA + lane_base + slot * 24 + cw0, v);
+            long long c3 = clock64();
+            tmem_st_wait();
+            long long c4 = clock64();
+            tc_fence_before();
+            __syncthreads();
+            long long c5 = clock64();
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    const uint64_t db = make_desc(smem_u32(sW) + i * 16 + ks * 2 * (CWROWS * 16), CWROWS * 16, 128, 0, 0);
+                    mma_i8_ts(tD + ks * 48, tA + slot * 24 + ks * 8, db, idesc, i > 0 ? 1u : 0u);
+                }
+                tc_commit(&bar[slot]);
+            }
+            long long c6 = clock64();
+            t_wait += c1 - c0; t_lds += c2 - c1; t_st += c3 - c2; t_stwait += c4 - c3; t_sync += c5 - c4; t_issue += c6 - c5;
+        }
+        for (int sl = 0; sl < 3; ++sl) { mbar_wait(&bar[sl], ph[sl]); ph[sl] ^= 1u; }
+        tc_fence_after();
+    }
+    if (tid == 0 && blockIdx.x == 0) {
+        a.acc[0] = t_wait; a.acc[1] = t_lds; a.acc[2] = t_st; a.acc[3] = t_stwait; a.acc[4] = t_sync; a.acc[5] = t_issue;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 256);
+}
 static uint32_t rng_state = 12345u;
 static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
 
@@ -588,6 +659,22 @@ int main(int argc, char **argv) {
     int dev = 0; cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
     printf("device %s, %d SMs, clock %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
     const int nsm = prop.multiProcessorCount;
+
+    if (argc > 1 && !strcmp(argv[1], "rowtime")) {
+        long long *dacc; CK(cudaMalloc(&dacc, 1024 * 8)); CK(cudaMemset(dacc, 0, 1024 * 8));
+        const int smem = 6 * CWROWS * 16 + CNA * CTANG + 4 * CTPITCH;
+        CK(cudaFuncSetAttribute(k_rowtime, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        for (int cps = 1; cps <= 2; ++cps) {
+            TimingArgs ta{nullptr, nullptr, dacc, 5, 100};
+            k_rowtime<<<nsm * cps, 128, smem>>>(ta);
+            CK(cudaDeviceSynchronize());
+            long long h[6]; CK(cudaMemcpy(h, dacc, 48, cudaMemcpyDeviceToHost));
+            const double rows = 100.0 * CS;
+            printf("rowtime %d CTA/SM (clk per row, thread 0): slot wait %.0f | 16 LDS %.0f | st issue %.0f | wait::st %.0f | fence+syncthreads %.0f | 3 MMA + commit %.0f | total %.0f\n",
+                   cps, h[0] / rows, h[1] / rows, h[2] / rows, h[3] / rows, h[4] / rows, h[5] / rows, (h[0] + h[1] + h[2] + h[3] + h[4] + h[5]) / rows);
+        }
+        return 0;
+    }
     // ---------------- checks
     std::vector<uint8_t> hA(128 * KB), hB(BROWS * KB);
     for (auto &v : hA) v = (uint8_t)(rnd() & 255);

@@ -217,6 +217,10 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     memset(&tg, 0, sizeof tg);
     bool use_tc = false;
     if (want_tc && pm_tc_geometry(s, Rmax, Wmax, n_angles, tg) && make_window_tensor_map(ctx, &tmap, 16, tg.load_rows)) use_tc = true;
+    // Measured (profiles/r02_ab_tc_vs_imma.txt): with one CTA per SM (tensor memory > 256 columns: search radius ~100) the
+    // latency-bound non-MAC phases make the tcgen05 kernel slower than the mma.sync kernel at three CTAs per SM, so the
+    // default takes it only where two CTAs fit; SID_PM_PATH=tc forces it.
+    if (use_tc && !path_env && tg.tmem_cols > 256) use_tc = false;
     bool smem_scratch = false;
     size_t smem = 0;
     int variant = 0;
@@ -238,7 +242,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
             const size_t maps_off = ((size_t)a.max_rr * 12 + 127) & ~(size_t)127;
             const size_t sq_bytes = 2 * (size_t)tg.npanels * (size_t)tg.wrows * 16;
             const bool fits_smem = maps_off + sq_bytes <= scratch;
-            const bool fits_tmem = 2 * tg.n16hmax + 8 <= tg.nacc * tg.n16max + tg.slotc && tg.n16hmax <= tg.wrows;
+            const bool fits_tmem = 2 * tg.n16hmax + 8 <= tg.nacc * tg.n16max + (tg.nslot - 2) * tg.slotc && tg.n16hmax <= tg.wrows;
             const char *e = getenv("SID_TC_MMA_SUMS");
             if (fits_smem && fits_tmem && !(e && e[0] == '0')) {
                 tg.mma_sums = 1; tg.sq_off = (int)maps_off; tg.wsq_off = (int)scratch;
@@ -338,8 +342,8 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         return fail(ctx, SID_ECUDA, msg);
     }
     if (getenv("SID_DEBUG"))
-        fprintf(stderr, "[sid] launch: tc=%d kidx=%d threads=%d smem=%zu occ(api)=%d tmem_cols=%d nab=%d ks=%d nacc=%d nb8=%d slotc=%d n16max=%d wrows=%d npanels=%d mma_sums=%d\n",
-                (int)use_tc, kidx, threads, smem, occ, tg.tmem_cols, tg.nab, tg.ks, tg.nacc, tg.nb8, tg.slotc, tg.n16max, tg.wrows, tg.npanels, tg.mma_sums);
+        fprintf(stderr, "[sid] launch: tc=%d kidx=%d threads=%d smem=%zu occ(api)=%d tmem_cols=%d nab=%d ks=%d nacc=%d nb8=%d slotc=%d nslot=%d n16max=%d wrows=%d npanels=%d mma_sums=%d\n",
+                (int)use_tc, kidx, threads, smem, occ, tg.tmem_cols, tg.nab, tg.ks, tg.nacc, tg.nb8, tg.slotc, tg.nslot, tg.n16max, tg.wrows, tg.npanels, tg.mma_sums);
     if (use_tc) {
         // The occupancy API answers 1 for a kernel that executes tcgen05.alloc with a run-time column count (it has to
         // assume all 512 columns); residency is really bounded by registers, shared memory and the columns we ask for.

@@ -41,6 +41,7 @@ struct PmTcCfg {
     int nissue;     // issuing warps per warp group = min(ks, 4)
     int nb8;        // 8-word groups a warp writes per Toeplitz row (its band of non-zero K words)
     int slotc;      // TMEM columns per A slot
+    int nslot;      // A slots shared by the two warp groups (3, or 2 when that keeps the allocation at 256 columns)
     int nacc;       // accumulators (K step ks adds into accumulator ks % nacc)
     int n16max;     // accumulator width: max N (result rows rounded up to 16)
     int tmem_cols;  // TMEM allocation (power of two)
@@ -80,8 +81,13 @@ inline bool pm_tc_geometry(int s, int Rmax, int Wmax, int n_angles, PmTcCfg &g) 
     g.slotc = (slotc + 7) & ~7;
     g.n16max = (Rmax + 15) & ~15;
     if (g.n16max > 256) return false;
-    g.nacc = (g.ks * g.n16max + 3 * g.slotc <= 256) ? g.ks : 1;
-    const int need = g.nacc * g.n16max + 3 * g.slotc;
+    // 256 columns keep two CTAs resident per SM: one accumulator per K step and three A slots if they fit, else one
+    // accumulator, else two slots (measured on cfg2: accumulator count and slot depth change the kernel by < 3 %)
+    g.nacc = g.ks; g.nslot = 3;
+    if (g.nacc * g.n16max + g.nslot * g.slotc > 256) g.nacc = 1;
+    if (g.nacc * g.n16max + g.nslot * g.slotc > 256) g.nslot = 2;
+    if (g.nacc * g.n16max + g.nslot * g.slotc > 256) g.nslot = 3;           // one CTA per SM anyway
+    const int need = g.nacc * g.n16max + g.nslot * g.slotc;
     if (need > 512) return false;
     g.tmem_cols = 32;
     while (g.tmem_cols < need) g.tmem_cols <<= 1;
@@ -298,7 +304,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
             const int n16h = (H + 15) & ~15;
             const uint32_t idesc_h = tc_idesc_u8(n16h);
             const uint32_t tQ = tD + (uint32_t)g.n16hmax;                    // second accumulator: sums of squares
-            const uint32_t tOnes = tA + (uint32_t)g.slotc, t255 = tA + (uint32_t)(2 * g.slotc);
+            const uint32_t tOnes = tA + (uint32_t)((g.nslot - 2) * g.slotc), t255 = tA + (uint32_t)((g.nslot - 1) * g.slotc);
             const int ntile_s = (RW + g.xt - 1) / g.xt;
             for (int tile = 0; tile < ntile_s; ++tile) {
                 const int xbase = tile * g.xt;
@@ -313,7 +319,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                     uint32_t z[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) z[c] = 0u;
-                    const int ncol = g.nacc * g.n16max + 3 * g.slotc, half = ((ncol / 8 + 1) / 2) * 8;
+                    const int ncol = g.nacc * g.n16max + g.nslot * g.slotc, half = ((ncol / 8 + 1) / 2) * 8;
                     const int cb = wg * half, ce = min(ncol, cb + half);
                     for (int c = cb; c < ce; c += 8) tc_st8(tD + lane_base + c, z);
                     tc_st_wait();
@@ -545,7 +551,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                     uint32_t z[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) z[c] = 0u;
-                    const int ncol = g.nacc * g.n16max + 3 * g.slotc, half = ((ncol / 8 + 1) / 2) * 8;
+                    const int ncol = g.nacc * g.n16max + g.nslot * g.slotc, half = ((ncol / 8 + 1) / 2) * 8;
                     const int cb = wg * half, ce = min(ncol, cb + half);
                     for (int c = cb; c < ce; c += 8) tc_st8(tD + lane_base + c, z);
                     tc_st_wait();
@@ -553,9 +559,10 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                 }
                 __syncthreads();
                 tc_fence_after();
-                // Row loop.  All index arithmetic is carried in running variables (i advances by 2): slot = i % 3,
-                // bi = i % 6 (the slot barrier this row commits to), bw = (i - 3) % 6 / kidx = (i - 3) / 6 (the barrier
-                // and completion index of the row that used this slot before).  Dead lanes read a row of zeros.
+                // Row loop.  All index arithmetic is carried in running variables (i advances by 2): slot = i % nslot,
+                // bi = i % (2 nslot) (the slot barrier this row commits to), bw = (i - nslot) % (2 nslot) and
+                // kidx = (i - nslot) / (2 nslot) (barrier and completion index of the row that used this slot before).
+                // Dead lanes read a row of zeros.
                 {
                     const bool issuer = lane == 0 && wiw < g.nissue;
                     const uint32_t sbar = smem_u32(&slot_bar[0]);
@@ -566,7 +573,8 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                     // this thread's first MMA of a row (K step wiw); further K steps (ks >= 4) are rare
                     const uint32_t d0 = tD + (uint32_t)((wiw % g.nacc) * g.n16max);
                     const uint64_t b0 = bdesc0 + (uint64_t)((p0 * PS) >> 4) + (uint64_t)(wiw * ((2 * PS) >> 4));
-                    int slot = wg, bi = wg, bw = wg + 3, kidx = -1;       // state for i = wg
+                    const int nsl = g.nslot, per = 2 * g.nslot;
+                    int slot = wg % nsl, bi = wg, bw = wg + nsl, kidx = -1;   // state for i = wg (bw, kidx describe row i - nslot)
                     if (g.nb8 == 2) {
                         // common case: 16 band words per row, held in registers one row ahead (the next row's shared-
                         // memory loads are in flight while this row's TMEM stores complete)
@@ -574,7 +582,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
 #pragma unroll
                         for (int c = 0; c < 16; ++c) v[c] = p[c];
                         for (int i = wg; i < s; i += 2) {
-                            if (i >= 3) {                        // MMAs of row i-3 (same slot, other warp group) done?
+                            if (i >= nsl) {                      // MMAs of row i - nslot (same slot) done?
                                 mbar_wait_addr(sbar + 8u * (uint32_t)bw, ((slot_par >> bw) + (unsigned)kidx) & 1u);
                                 tc_fence_after();
                             }
@@ -602,13 +610,13 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                                                  b0 + (uint64_t)(i + (ks - wiw) * ((2 * PS) >> 4)), idesc, 1u);
                                 tc_commit_addr(sbar + 8u * (uint32_t)bi);
                             }
-                            slot = slot >= 1 ? slot - 1 : 2;     // (slot + 2) % 3
-                            bi += 2; if (bi >= 6) bi -= 6;
-                            bw += 2; if (bw >= 6) { bw -= 6; ++kidx; }
+                            slot += 2; if (slot >= nsl) slot -= nsl;     // (slot + 2) % nslot
+                            bi += 2; if (bi >= per) bi -= per;
+                            bw += 2; if (bw >= per) { bw -= per; ++kidx; }
                         }
                     } else {
                     for (int i = wg; i < s; i += 2) {
-                        if (i >= 3) {                            // MMAs of row i-3 (same slot, other warp group) done?
+                        if (i >= nsl) {                          // MMAs of row i - nslot (same slot) done?
                             mbar_wait_addr(sbar + 8u * (uint32_t)bw, ((slot_par >> bw) + (unsigned)kidx) & 1u);
                             tc_fence_after();
                         }
@@ -632,15 +640,15 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                             tc_commit_addr(sbar + 8u * (uint32_t)bi);
                         }
                         p += pstep;
-                        slot = slot >= 1 ? slot - 1 : 2;         // (slot + 2) % 3
-                        bi += 2; if (bi >= 6) bi -= 6;
-                        bw += 2; if (bw >= 6) { bw -= 6; ++kidx; }
+                        slot += 2; if (slot >= nsl) slot -= nsl;         // (slot + 2) % nslot
+                        bi += 2; if (bi >= per) bi -= per;
+                        bw += 2; if (bw >= per) { bw -= per; ++kidx; }
                     }
                     }
                 }
                 if (lane == 0 && wiw < g.nissue) tc_commit(&done_bar[wg]);
-                for (int b = 0; b < 6; ++b)                      // completions this tile added to each slot barrier
-                    if (b < s) slot_par ^= (unsigned)(((s - b + 5) / 6) & 1) << b;
+                for (int b = 0; b < 2 * g.nslot; ++b)            // completions this tile added to each slot barrier
+                    if (b < s) slot_par ^= (unsigned)(((s - b + 2 * g.nslot - 1) / (2 * g.nslot)) & 1) << b;
                 mbar_wait(&done_bar[0], done_phase);
                 mbar_wait(&done_bar[1], done_phase);
                 done_phase ^= 1u;

@@ -33,7 +33,7 @@ def test_reference_arm_json_line():
 
 @pytest.mark.gpu
 def test_product_arm_json_line():
-    d = run_bench("--steps", "3", "--warmup", "3", "--side", "1500", "--grid", "30", "--cpu-sample", "200")
+    d = run_bench("--steps", "3", "--warmup", "3", "--side", "1500", "--grid", "30", "--cpu-sample", "200", "--no-configs")
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline", "parity"} <= set(d)
     assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "u8" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["gpu_launches"] >= d["steps"]
@@ -45,5 +45,11 @@ def test_product_arm_json_line():
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     p = d["parity"]
     assert p["nan_pattern_equal"] and p["position_angle_equal"] == p["compared"] == p["r_bit_equal"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] > 0
+    if d["cpu_baseline"]["kind"] == "reference":            # the reference copy travelled: parity is reported against it too
+        v = p["vs_reference"]
+        assert v["nan_pattern_equal"] and v["unexplained"] == 0 and v["max_abs_dr"] <= 1e-4
+        assert {"max_abs_dh", "n_dh_above_1e-4", "tie_explained", "position_angle_exact"} <= set(v)
+    assert "e2e_pageable" in d and d["e2e_pageable"]["value"] > 0
+    assert d["configs"] is None or {"cfg1", "cfg3", "cfg4"} <= set(d["configs"])
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -403,3 +403,53 @@ def test_image_narrower_than_tma_box_and_corner_windows(gpu_ctx):
     ref, st2 = co.use_mcc_batch(c, r, c2, r2, b, img1, img2, 35, 0.0, angles=[-3, 0, 3])
     assert_equals_exact_oracle(got, ref, st, st2)
     assert (st == 1).sum() >= 1
+
+
+def test_series_honours_the_reference_defaults_and_flag_kwargs():
+    """use_mcc_series without kwargs uses the reference's defaults (hes_norm=True, pmlib.py:36) and forwards
+    hes_norm / hes_smth / mcc_norm / rot_order like use_mcc_batch does (round-1 advisor finding)."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=31, side=900, grid=12)
+    pairs = [(img1, img2, c1, r1, c2, r2, b)]
+    for kw in ({}, dict(hes_norm=False), dict(hes_smth=True), dict(mcc_norm=True, angles=[-3, 3]),
+               dict(rot_order=1, hes_smth=True, mcc_norm=True)):
+        table = sharding.use_mcc_series(pairs, 35, 0.0, **kw)[0]
+        batch = sid.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0, **kw)
+        assert np.array_equal(table, batch, equal_nan=True), kw
+        opts = dict(rot_order=kw.get("rot_order", 0), hes_norm=kw.get("hes_norm", True), hes_smth=kw.get("hes_smth", False),
+                    mcc_norm=kw.get("mcc_norm", False))
+        ref, _ = co.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=kw.get("angles", [-3, 0, 3]), **opts)
+        assert_equals_exact_oracle(table, ref)
+
+
+def test_pair_is_uploaded_on_every_call_unless_resident_is_requested():
+    """No identity guessing: an in-place edit of the image (masking, the usual step between two calls) is seen by the
+    next call; resident=True is the explicit way to skip the upload."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=33, side=1024, grid=10)   # 1024 rows: the old sampled
+    first = sid.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0)                            # checksum hit column 0 only
+    img1 = img1.copy()
+    img1[400:600, 400:600] = 0                                        # in-place style edit, same shape / dtype
+    second = sid.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0)
+    ref, _ = co.use_mcc_batch(c1, r1, c2, r2, b, img1, img2, 35, 0.0, angles=[-3, 0, 3])
+    assert_equals_exact_oracle(second, ref)
+    assert np.isnan(second[:, 0]).sum() > np.isnan(first[:, 0]).sum()
+    again = sid.use_mcc_batch(c1, r1, c2, r2, b, None, None, 35, 0.0, resident=True)     # images not even passed
+    assert np.array_equal(again, second, equal_nan=True)
+
+
+def test_tcgen05_path_equals_legacy_paths_bit_for_bit(gpu_ctx):
+    """The three correlation paths -- tcgen05.mma kind::i8 (default), mma.sync (SID_PM_PATH=imma) and the integer pipe
+    (SID_PM_PATH=dp4a) -- must agree bit for bit, including x-tiled result maps, even sizes and 21-angle batches."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=35, side=1500, grid=22)
+    rng = np.random.default_rng(2)
+    gpu_ctx.set_pair(img1, img2)
+    for s, angles, lo, hi in ((35, [-3, 0, 3], 20, 50), (50, [-2, 2], 20, 30), (35, list(range(-10, 11)), 20, 22), (51, [0], 60, 100)):
+        brd = np.floor(rng.uniform(lo, hi + 1, len(c1)))
+        tables = {}
+        for path in ("tc", "imma", "dp4a"):
+            os.environ["SID_PM_PATH"] = path
+            try:
+                tables[path] = gpu_ctx.run(c1, r1, c2, r2, brd, s, angles, 0.5)
+            finally:
+                del os.environ["SID_PM_PATH"]
+        assert np.array_equal(tables["tc"], tables["imma"], equal_nan=True), (s, len(angles))
+        assert np.array_equal(tables["tc"], tables["dp4a"], equal_nan=True), (s, len(angles))
