@@ -95,6 +95,10 @@ int sid_adopt_pair_device(sid_ctx *ctx,
                           uint8_t *d_img1, int rows1, int cols1, int64_t pitch1, int64_t bytes1,
                           uint8_t *d_img2, int rows2, int cols2, int64_t pitch2, int64_t bytes2);
 
+/* Asynchronous 2-D host -> device copy of `rows` image rows on the context's stream (a rank's row slab of the
+ * pair, before the all-gather that completes the adopted buffers). */
+int sid_upload_rows(sid_ctx *ctx, uint8_t *d_dst, int64_t dst_pitch, const uint8_t *src, int64_t src_pitch, int cols, int rows);
+
 /* use_mcc for n grid points (host arrays in, host array out, synchronous).
  *   c1, r1        float pixel coordinates on image 1
  *   c2fg, r2fg    integer-valued first guess on image 2

@@ -22,7 +22,7 @@ SID_HES_NORM, SID_HES_SMTH, SID_MCC_NORM = 1, 2, 4
 
 EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
-    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
+    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_upload_rows", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
     "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian", "sid_knn_hamming2",
     "sid_deformation",
 ]
@@ -63,6 +63,7 @@ def load_library():
         lib.sid_pair_layout.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.sid_adopt_pair_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                               C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64]
+        lib.sid_upload_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int]
         lib.sid_run.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
         lib.sid_run_pair.argtypes = pair + [C.c_int64] + [C.c_void_p] * 5 + \
@@ -201,6 +202,14 @@ class Context(object):
             C.c_void_p(ptr2), shape2[0], shape2[1], pitch2, bytes2))
         self._pair_key = None
         return self
+
+    def upload_rows(self, dst_ptr, dst_pitch, rows_array):
+        """Asynchronous 2-D upload of image rows (uint8, unit column stride) to ``dst_ptr`` on the context's stream."""
+        a = as_u8_image(rows_array) if rows_array.shape[0] else rows_array
+        if a.shape[0]:
+            self._check(self._lib.sid_upload_rows(self._h, C.c_void_p(dst_ptr), dst_pitch, a.ctypes.data, a.strides[0],
+                                                  a.shape[1], a.shape[0]))
+        return a.shape[0] * a.shape[1]
 
     def run(self, c1, r1, c2fg, r2fg, border, img_size, angles, alpha0, rot_order=0, flags=SID_HES_NORM,
             mtype=SID_TM_CCOEFF_NORMED, want_status=False):

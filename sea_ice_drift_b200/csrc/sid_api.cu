@@ -518,6 +518,10 @@ int sid_adopt_pair_device(sid_ctx *ctx, uint8_t *d_img1, int rows1, int cols1, i
     if (bytes1 < pitch1 * (int64_t)rows1 + (int64_t)IMG_TAIL_SLACK || bytes2 < pitch2 * (int64_t)rows2 + (int64_t)IMG_TAIL_SLACK)
         return fail(ctx, SID_EINVAL, "adopted images need the tail slack of sid_pair_layout");
     CU(cudaSetDevice(ctx->device));
+    if (ctx->have_pair && !ctx->img1.owned && !ctx->img2.owned && ctx->img1.p == d_img1 && ctx->img2.p == d_img2 &&
+        ctx->rows1 == rows1 && ctx->cols1 == cols1 && ctx->pitch1 == pitch1 && ctx->rows2 == rows2 && ctx->cols2 == cols2 &&
+        ctx->pitch2 == pitch2)
+        return SID_OK;                                          // the same buffers again (refilled in place by the caller)
     CU(cudaStreamSynchronize(ctx->stream));                    // nothing in flight still reads the old pair
     DevBuf *bufs[2] = {&ctx->img1, &ctx->img2};
     for (DevBuf *b : bufs) { if (b->p && b->owned) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
@@ -526,6 +530,15 @@ int sid_adopt_pair_device(sid_ctx *ctx, uint8_t *d_img1, int rows1, int cols1, i
     ctx->rows1 = rows1; ctx->cols1 = cols1; ctx->pitch1 = pitch1;
     ctx->rows2 = rows2; ctx->cols2 = cols2; ctx->pitch2 = pitch2;
     ctx->have_pair = true;
+    return SID_OK;
+}
+
+int sid_upload_rows(sid_ctx *ctx, uint8_t *d_dst, int64_t dst_pitch, const uint8_t *src, int64_t src_pitch, int cols, int rows) {
+    if (!ctx) return SID_EINVAL;
+    if (rows == 0) return SID_OK;
+    if (!d_dst || !src || cols <= 0 || rows < 0 || dst_pitch < cols || src_pitch < cols) return fail(ctx, SID_EINVAL, "bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy2DAsync(d_dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice, ctx->stream));
     return SID_OK;
 }
 

@@ -114,8 +114,10 @@ def _split_buffer(key, plan, device):
 def replicate_pair(img1, img2, dist, ctx=None, device=None):
     """Make ``img1`` / ``img2`` resident on EVERY rank's GPU while each rank transfers only 1/world of them over
     PCIe: rank r copies rows ``SplitPlan.row_range(r)`` of both images host -> device into its slab of the padded
-    buffers, then one in-place ``all_gather_into_tensor`` per image fills the rest over NVLink.  The context adopts
-    the buffers without a copy (``sid_adopt_pair_device``).  Returns the bytes this rank uploaded."""
+    buffers (one asynchronous 2-D copy per image on the compute stream), then one in-place
+    ``all_gather_into_tensor`` per image fills the rest over NVLink -- image 1's all-gather runs while image 2's
+    slab is still uploading.  The context adopts the buffers without a copy (``sid_adopt_pair_device``).  Returns
+    (bytes this rank uploaded, [(buffer, plan), (buffer, plan)])."""
     import torch
     from . import _lib
     ctx = ctx or _lib.default_context(device)
@@ -130,28 +132,39 @@ def replicate_pair(img1, img2, dist, ctx=None, device=None):
         buf = _split_buffer((ctx.device if nccl else 'cpu', k), plan, dev)
         r0, r1 = plan.row_range(rank)
         mine = buf[rank * plan.slab:(rank + 1) * plan.slab]
-        if r1 > r0:
-            src = torch.from_numpy(img[r0:r1])
-            mine.view(plan.rows_per, plan.pitch)[:r1 - r0, :plan.cols].copy_(src, non_blocking=True)
+        if nccl:
+            uploaded += ctx.upload_rows(mine.data_ptr(), plan.pitch, img[r0:r1])
+        elif r1 > r0:
+            mine.view(plan.rows_per, plan.pitch)[:r1 - r0, :plan.cols].copy_(torch.from_numpy(img[r0:r1]))
             uploaded += (r1 - r0) * plan.cols
         whole = buf[:plan.gather_bytes]
         # in place: NCCL's all-gather is in place when the send buffer is the rank's own slot of the receive buffer
         dist.all_gather_into_tensor(whole, mine if nccl else mine.clone())
         bufs.append((buf, plan))
     if nccl:
-        torch.cuda.current_stream(dev).synchronize()
         (b1, p1), (b2, p2) = bufs
         ctx.adopt_pair_device(b1.data_ptr(), (p1.rows, p1.cols), p1.pitch, b1.numel(),
                               b2.data_ptr(), (p2.rows, p2.cols), p2.pitch, b2.numel())
     return uploaded, bufs
 
 
+def shard_all(border, world):
+    """``shard_indices`` of every rank from ONE sort."""
+    border = np.asarray(border, dtype=np.float64)
+    if border.size and border.min() == border.max():             # uniform radius: the stable sort is the identity
+        return [np.arange(r, border.size, world) for r in range(world)]
+    order = np.argsort(-border, kind='stable')
+    return [np.sort(order[r::world]) for r in range(world)]
+
+
 def use_mcc_batch_split(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0, **kwargs):
     """``use_mcc_batch`` for ONE pair over all ranks of the NCCL process group (north_star's split): the pair is
     replicated by :func:`replicate_pair` (1/world of it per PCIe link + one all-gather over NVLink), the points are
     dealt by :func:`shard_indices`, every rank's kernel writes its rows into its slab of the result buffer and one
-    ``all_gather_into_tensor`` assembles the (N, 5) table on every rank.  Every rank passes the same arguments.
-    Falls back to :func:`use_mcc_batch_sharded` (each rank uploads the whole pair) without NCCL."""
+    ``all_gather_into_tensor`` assembles the (N, 5) table on every rank.  Everything is enqueued on torch's current
+    stream (slab copies, collectives, kernels), so the only host synchronisation is the final read-back.  Every rank
+    passes the same arguments.  Falls back to :func:`use_mcc_batch_sharded` (each rank uploads the whole pair)
+    without NCCL."""
     dist = _dist()
     n = len(c1)
     if dist is None or dist.get_backend() != 'nccl' or n == 0:
@@ -161,31 +174,37 @@ def use_mcc_batch_split(c1, r1, c2fg, r2fg, border, img1, img2, img_size, alpha0
     ctx = _lib.default_context(kwargs.get('device'))
     dev = torch.device('cuda', ctx.device)
     rank, world = dist.get_rank(), dist.get_world_size()
-    replicate_pair(img1, img2, dist, ctx)
-    border = np.asarray(border, dtype=np.float64)
-    idx = shard_indices(border, world, rank)
-    n_max = -(-n // world)
-    pts = np.zeros((5, n_max), dtype=np.float64)
-    for k, arr in enumerate((c1, r1, c2fg, r2fg, border)):
-        pts[k, :len(idx)] = np.asarray(arr, dtype=np.float64)[idx]
-    pts[:, len(idx):] = np.nan                                    # padding rows: rejected up front, NaN out
-    d_pts = torch.from_numpy(pts).to(dev)
-    table = torch.empty((world, n_max, 5), dtype=torch.float64, device=dev)
-    flags = _lib.flags_from_kwargs(kwargs.get('hes_norm', True), kwargs.get('hes_smth', False), kwargs.get('mcc_norm', False))
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
     try:
-        ctx.run_device(n_max, *[d_pts[k].data_ptr() for k in range(5)], int(np.nanmax(border)) if n else 1, img_size,
+        replicate_pair(img1, img2, dist, ctx)
+        border = np.asarray(border, dtype=np.float64)
+        parts = shard_all(border, world)
+        idx = parts[rank]
+        n_max = -(-n // world)
+        pts = np.full((5, n_max), np.nan, dtype=np.float64)           # padding rows: rejected up front, NaN out
+        for k, arr in enumerate((c1, r1, c2fg, r2fg, border)):
+            pts[k, :len(idx)] = np.asarray(arr, dtype=np.float64)[idx]
+        d_pts = torch.from_numpy(pts).to(dev, non_blocking=True)
+        table = torch.empty((world, n_max, 5), dtype=torch.float64, device=dev)
+        flags = _lib.flags_from_kwargs(kwargs.get('hes_norm', True), kwargs.get('hes_smth', False), kwargs.get('mcc_norm', False))
+        ctx.run_device(n_max, *[d_pts[k].data_ptr() for k in range(5)], int(np.nanmax(border)), img_size,
                        list(kwargs.get('angles', [-3, 0, 3])), alpha0, table[rank].data_ptr(),
                        rot_order=kwargs.get('rot_order', 0), flags=flags, mtype=kwargs.get('mtype', _lib.SID_TM_CCOEFF_NORMED))
         dist.all_gather_into_tensor(table.view(world * n_max, 5), table[rank])        # in place, the ONE result collective
-        host = table.cpu().numpy()
+        host_t = _staging('split_recv', (world, n_max, 5), dev)
+        host_t.copy_(table, non_blocking=True)
+        stream.synchronize()
+        host = host_t.numpy()
     finally:
         ctx.set_stream(None)
-    out = np.full((n, 5), np.nan, dtype=np.float64)
+    out = np.empty((n, 5), dtype=np.float64)
+    uniform = border.min() == border.max()
     for r in range(world):
-        ridx = shard_indices(border, world, r)
-        out[ridx] = host[r, :len(ridx)]
+        if uniform:
+            out[r::world] = host[r, :len(parts[r])]                   # strided slab: a plain strided copy
+        else:
+            out[parts[r]] = host[r, :len(parts[r])]
     return out
 
 
