@@ -95,6 +95,19 @@ int sid_adopt_pair_device(sid_ctx *ctx,
                           uint8_t *d_img1, int rows1, int cols1, int64_t pitch1, int64_t bytes1,
                           uint8_t *d_img2, int rows2, int cols2, int64_t pitch2, int64_t bytes2);
 
+/* Post-processing of pattern_matching for AFFINE geolocation (reference pmlib.py:462-497 and lib.py:408-412), on the
+ * device: sub-pixel remainder c2 += c2pm1 - round(c2pm1), pixel -> destination x/y and lon/lat, u = x2 - x1,
+ * v = y2 - y1, and the _fill_gpi scatter into NaN-filled grids.
+ *   n_valid, grid_index  the valid grid points (gpi) in table order and their flat grid positions
+ *   c2pm1, r2pm1         n_grid image-2 pixel coordinates of the grid (host)
+ *   results              host (n_valid, 5) table, or NULL: use the table the previous sid_run / sid_run_pair left on
+ *                        the device (those accept out == NULL, so the table never visits the host)
+ *   xy, ll               2 x 3 row-major affine maps pixel -> destination x/y and pixel -> lon/lat: m0*c + m1*r + m2
+ *   out                  host, 7 x n_grid doubles: u, v, a, r, h, lon2, lat2                                         */
+int sid_pm_epilogue_affine(sid_ctx *ctx, int64_t n_valid, const int32_t *grid_index, int64_t n_grid,
+                           const double *c2pm1, const double *r2pm1, const double *results,
+                           const double *xy, const double *ll, double *out);
+
 /* Asynchronous 2-D host -> device copy of `rows` image rows on the context's stream (a rank's row slab of the
  * pair, before the all-gather that completes the adopted buffers). */
 int sid_upload_rows(sid_ctx *ctx, uint8_t *d_dst, int64_t dst_pitch, const uint8_t *src, int64_t src_pitch, int cols, int rows);

@@ -4,8 +4,10 @@ import csv
 import sys
 
 path, npts = sys.argv[1], float(sys.argv[2])
+only = sys.argv[3] if len(sys.argv) > 3 else None          # keep only functions whose name contains this
 rows = list(csv.reader(open(path)))
 cur = None
+keep = True
 per_line = {}
 hdr = None
 for r in rows:
@@ -15,11 +17,12 @@ for r in rows:
         cur = r[1].split("/")[-1]
         continue
     if r[0] == "Function Name":
+        keep = only is None or only in r[1]
         continue
     if r[0] == "Line No":
         hdr = {k: i for i, k in enumerate(r)}
         continue
-    if hdr is None or r[2] != "-":       # aggregated source-line rows carry "-" in the Address column
+    if hdr is None or r[2] != "-" or not keep:       # aggregated source-line rows carry "-" in the Address column
         continue
     try:
         ln = int(r[0])

@@ -22,7 +22,7 @@ SID_HES_NORM, SID_HES_SMTH, SID_MCC_NORM = 1, 2, 4
 
 EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
-    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_upload_rows", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
+    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_upload_rows", "sid_pm_epilogue_affine", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
     "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian", "sid_knn_hamming2",
     "sid_deformation",
 ]
@@ -63,6 +63,7 @@ def load_library():
         lib.sid_pair_layout.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.sid_adopt_pair_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                               C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64]
+        lib.sid_pm_epilogue_affine.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         lib.sid_upload_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int]
         lib.sid_run.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
@@ -203,6 +204,23 @@ class Context(object):
         self._pair_key = None
         return self
 
+    def pm_epilogue_affine(self, gpi, c2pm1, r2pm1, xy, ll, results=None):
+        """pattern_matching's post-processing for affine geolocation on the device (sid_pm_epilogue_affine): returns
+        the seven flat grids u, v, a, r, h, lon2, lat2 (NaN outside ``gpi``).  ``results`` None: use the table the
+        previous run left on the device."""
+        gpi = np.asarray(gpi, dtype=bool).ravel()
+        idx = np.ascontiguousarray(np.flatnonzero(gpi), dtype=np.int32)
+        c = np.ascontiguousarray(c2pm1, dtype=np.float64).ravel()
+        r = np.ascontiguousarray(r2pm1, dtype=np.float64).ravel()
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(6)
+        ll = np.ascontiguousarray(ll, dtype=np.float64).reshape(6)
+        res = None if results is None else np.ascontiguousarray(results, dtype=np.float64).reshape(-1, 5)
+        out = np.empty((7, gpi.size), dtype=np.float64)
+        self._check(self._lib.sid_pm_epilogue_affine(
+            self._h, idx.size, idx.ctypes.data, gpi.size, c.ctypes.data, r.ctypes.data,
+            None if res is None else res.ctypes.data, xy.ctypes.data, ll.ctypes.data, out.ctypes.data))
+        return out
+
     def upload_rows(self, dst_ptr, dst_pitch, rows_array):
         """Asynchronous 2-D upload of image rows (uint8, unit column stride) to ``dst_ptr`` on the context's stream."""
         a = as_u8_image(rows_array) if rows_array.shape[0] else rows_array
@@ -212,7 +230,7 @@ class Context(object):
         return a.shape[0] * a.shape[1]
 
     def run(self, c1, r1, c2fg, r2fg, border, img_size, angles, alpha0, rot_order=0, flags=SID_HES_NORM,
-            mtype=SID_TM_CCOEFF_NORMED, want_status=False):
+            mtype=SID_TM_CCOEFF_NORMED, want_status=False, keep_on_device=False):
         arrs = [np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64) for x in (c1, r1, c2fg, r2fg, border)]
         n = arrs[0].size
         if any(a.size != n for a in arrs):
@@ -223,11 +241,14 @@ class Context(object):
         status = np.zeros(n, dtype=np.int32)
         self._check(self._lib.sid_run(
             self._h, n, *[a.ctypes.data for a in arrs], int(img_size), len(ang), ang.ctypes.data,
-            tab.ctypes.data, int(rot_order), int(flags), int(mtype), out.ctypes.data, status.ctypes.data))
+            tab.ctypes.data, int(rot_order), int(flags), int(mtype), None if keep_on_device else out.ctypes.data,
+            status.ctypes.data))
+        if keep_on_device:
+            return status if want_status else None
         return (out, status) if want_status else out
 
     def run_pair(self, img1, img2, c1, r1, c2fg, r2fg, border, img_size, angles, alpha0, rot_order=0,
-                 flags=SID_HES_NORM, mtype=SID_TM_CCOEFF_NORMED, want_status=False):
+                 flags=SID_HES_NORM, mtype=SID_TM_CCOEFF_NORMED, want_status=False, keep_on_device=False):
         """Upload the pair and match all points in one call, copy overlapped with compute."""
         img1, img2 = as_u8_image(img1), as_u8_image(img2)
         arrs = [np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64) for x in (c1, r1, c2fg, r2fg, border)]
@@ -242,8 +263,11 @@ class Context(object):
             self._h, img1.ctypes.data, img1.shape[0], img1.shape[1], img1.strides[0],
             img2.ctypes.data, img2.shape[0], img2.shape[1], img2.strides[0],
             n, *[a.ctypes.data for a in arrs], int(img_size), len(ang), ang.ctypes.data,
-            tab.ctypes.data, int(rot_order), int(flags), int(mtype), out.ctypes.data, status.ctypes.data))
+            tab.ctypes.data, int(rot_order), int(flags), int(mtype), None if keep_on_device else out.ctypes.data,
+            status.ctypes.data))
         self._pair_key = None
+        if keep_on_device:
+            return status if want_status else None
         return (out, status) if want_status else out
 
     def run_device(self, n, d_c1, d_r1, d_c2fg, d_r2fg, d_border, max_border, img_size, angles, alpha0,

@@ -52,11 +52,12 @@ struct sid_ctx {
     long long pitch1 = 0, pitch2 = 0;
     bool have_pair = false;
     // per-call buffers
-    DevBuf pts, order, out, status, angles, scratch, counter, misc, tail_maps, tail_recs;
+    DevBuf pts, order, out, status, angles, scratch, counter, misc, tail_maps, tail_recs, epi;
     void *pin = nullptr;
     size_t pin_cap = 0;
     cudaEvent_t k_ev[2] = {};                // bracket the last fused-kernel launch (sid_last_kernel_ms)
     bool k_ev_valid = false;
+    long long table_n = -1;                  // rows of the result table the last sid_run / sid_run_pair left in `out`
     long long tail_hint_n = 0;               // total points of the current host call (sizes the tail hand-off once)
     // staged upload of pageable host images (sid_run_pair): pinned double buffer + "slot free again" events
     void *stage = nullptr;
@@ -434,7 +435,7 @@ void sid_destroy(sid_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->img1, &ctx->img2, &ctx->pts, &ctx->order, &ctx->out, &ctx->status,
-                      &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs};
+                      &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs, &ctx->epi};
     for (DevBuf *b : bufs) if (b->p && b->owned) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -602,7 +603,7 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
     int rc = check_common(ctx, img_size, n_angles, angle_tab, rot_order, mtype);
     if (rc) return rc;
     if (!pair && !ctx->have_pair) return fail(ctx, SID_ENOPAIR, "sid_set_pair has not been called");
-    if (n < 0 || (n > 0 && (!c1 || !r1 || !c2fg || !r2fg || !border || !out)) || !angles)
+    if (n < 0 || (n > 0 && (!c1 || !r1 || !c2fg || !r2fg || !border)) || !angles)
         return fail(ctx, SID_EINVAL, "null point array");
     if (n > 0x7fffffffLL) return fail(ctx, SID_EINVAL, "too many points");
     CU(cudaSetDevice(ctx->device));
@@ -779,11 +780,12 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
     if (pair) ctx->have_pair = true;
     double *hout = (double *)((char *)ctx->pin + pts_bytes + ord_bytes);
     int *hst = (int *)((char *)hout + out_bytes);
-    CU(cudaMemcpyAsync(hout, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->table_n = n;                                          // the (n, 5) table stays in ctx->out for sid_pm_epilogue_affine
+    if (out) CU(cudaMemcpyAsync(hout, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (status) CU(cudaMemcpyAsync(hst, ctx->status.p, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
-    memcpy(out, hout, out_bytes);
+    if (out) memcpy(out, hout, out_bytes);
     if (status) memcpy(status, hst, st_bytes);
     return SID_OK;
 }
@@ -830,6 +832,68 @@ int sid_run_device(sid_ctx *ctx, int64_t n, const double *d_c1, const double *d_
     if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab))) return rc;
     return launch_pm(ctx, n, d_c1, d_r1, d_c2fg, d_r2fg, d_border, nullptr, max_border, max_border, img_size,
                      n_angles, d_angles, d_tab, rot_order, flags, d_out, d_status);
+}
+
+// ------------------------------------------------------------------ post-processing epilogue
+namespace {
+__device__ __forceinline__ double affine_eval(const double *m, double c, double r) {      // (m0*c + m1*r) + m2, NumPy's order, no FMA
+    return __dadd_rn(__dadd_rn(__dmul_rn(m[0], c), __dmul_rn(m[1], r)), m[2]);
+}
+__global__ void pm_epilogue_fill_kernel(double *out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = nan("");
+}
+struct EpiArgs { double xy[6]; double ll[6]; };
+// reference pmlib.py:462-497: sub-pixel remainder, pixel -> x/y and lon/lat, u = x2 - x1, v = y2 - y1, _fill_gpi scatter
+__global__ void pm_epilogue_kernel(long long n_valid, const int *gidx, const double *res, const double *c2pm1, const double *r2pm1,
+                                   const EpiArgs e, long long n_grid, double *out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_valid) return;
+    const long long g = gidx[k];
+    const double c = c2pm1[g], r = r2pm1[g];
+    const double c2 = __dadd_rn(res[5 * k], __dsub_rn(c, rint(c)));          // results[:, 0] + (c2pm1 - round(c2pm1))[gpi]
+    const double r2 = __dadd_rn(res[5 * k + 1], __dsub_rn(r, rint(r)));
+    out[g] = __dsub_rn(affine_eval(e.xy, c2, r2), affine_eval(e.xy, c, r));
+    out[n_grid + g] = __dsub_rn(affine_eval(e.xy + 3, c2, r2), affine_eval(e.xy + 3, c, r));
+    out[2 * n_grid + g] = res[5 * k + 2];
+    out[3 * n_grid + g] = res[5 * k + 3];
+    out[4 * n_grid + g] = res[5 * k + 4];
+    out[5 * n_grid + g] = affine_eval(e.ll, c2, r2);
+    out[6 * n_grid + g] = affine_eval(e.ll + 3, c2, r2);
+}
+}  // namespace
+
+int sid_pm_epilogue_affine(sid_ctx *ctx, int64_t n_valid, const int32_t *grid_index, int64_t n_grid, const double *c2pm1,
+                           const double *r2pm1, const double *results, const double *xy, const double *ll, double *out) {
+    if (!ctx) return SID_EINVAL;
+    if (n_valid < 0 || n_grid <= 0 || n_valid > n_grid || (n_valid > 0 && !grid_index) || !c2pm1 || !r2pm1 || !xy || !ll || !out)
+        return fail(ctx, SID_EINVAL, "bad epilogue arguments");
+    if (!results && ctx->table_n != n_valid)
+        return fail(ctx, SID_EINVAL, "no device result table of that length (run sid_run / sid_run_pair first, or pass results)");
+    CU(cudaSetDevice(ctx->device));
+    const size_t b_idx = ((size_t)n_valid * 4 + 255) & ~(size_t)255, b_grid = ((size_t)n_grid * 8 + 255) & ~(size_t)255;
+    const size_t b_res = results ? (((size_t)n_valid * 40 + 255) & ~(size_t)255) : 0, b_out = (size_t)n_grid * 56;
+    int rc = reserve(ctx, ctx->epi, b_idx + 2 * b_grid + b_res + b_out);
+    if (rc) return rc;
+    char *base = (char *)ctx->epi.p;
+    int *d_idx = (int *)base;
+    double *d_c = (double *)(base + b_idx), *d_r = (double *)(base + b_idx + b_grid);
+    double *d_res = results ? (double *)(base + b_idx + 2 * b_grid) : (double *)ctx->out.p;
+    double *d_out = (double *)(base + b_idx + 2 * b_grid + b_res);
+    if (n_valid) CU(cudaMemcpyAsync(d_idx, grid_index, (size_t)n_valid * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_c, c2pm1, (size_t)n_grid * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_r, r2pm1, (size_t)n_grid * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (results && n_valid) CU(cudaMemcpyAsync(d_res, results, (size_t)n_valid * 40, cudaMemcpyHostToDevice, ctx->stream));
+    EpiArgs e;
+    memcpy(e.xy, xy, sizeof e.xy);
+    memcpy(e.ll, ll, sizeof e.ll);
+    pm_epilogue_fill_kernel<<<(unsigned)((7 * n_grid + 255) / 256), 256, 0, ctx->stream>>>(d_out, 7 * n_grid);
+    if (n_valid) pm_epilogue_kernel<<<(unsigned)((n_valid + 255) / 256), 256, 0, ctx->stream>>>(n_valid, d_idx, d_res, d_c, d_r, e, n_grid, d_out);
+    ctx->launches += n_valid ? 2 : 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, b_out, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SID_OK;
 }
 
 // ------------------------------------------------------------------ single-call entry points

@@ -253,7 +253,23 @@ def pattern_matching(lon_pm1, lat_pm1, n1, c1, r1, n2, c2, r2,
            (r1pm1i + hws_hypot + margin < shape1[0]))
     alpha0 = get_initial_rotation(n1, n2)
 
-    from .sharding import use_mcc_batch_sharded
+    from .sharding import use_mcc_batch_sharded, _dist
+    # Affine geolocation (an object exposing ``affine_maps(srs) -> (pixel->x/y, pixel->lon/lat)`` 2 x 3 matrices, e.g.
+    # synthetic.ArrayDomain): the post-processing below (reference pmlib.py:462-497) runs on the device too, on the
+    # table the kernels left there -- the (N, 5) table never visits the host.  Real Nansat objects (GDAL, possibly
+    # thin-plate-spline geolocation) take the host path.
+    affine = getattr(n2, 'affine_maps', None)
+    if (affine is not None and _dist() is None and kwargs.get('device_epilogue', True) and gpi.any()
+            and _is_builtin_matcher(kwargs.get('template_matcher'))):
+        xy, ll = affine(srs)
+        ctx = _ctx(kwargs)
+        flags = flags_from_kwargs(kwargs.get('hes_norm', True), kwargs.get('hes_smth', False), kwargs.get('mcc_norm', False))
+        ctx.run_pair(img1, img2, c1pm1i[gpi], r1pm1i[gpi], c2fg[gpi], r2fg[gpi], brd2[gpi], img_size,
+                     list(kwargs.get('angles', [-3, 0, 3])), alpha0, kwargs.get('rot_order', 0), flags,
+                     kwargs.get('mtype', TM_CCOEFF_NORMED), keep_on_device=True)
+        grids = ctx.pm_epilogue_affine(gpi, c2pm1, r2pm1, xy, ll)
+        print('\n', 'Pattern matching - OK! (%3.0f sec)' % (time.time() - t0))
+        return tuple(grid.reshape(dst_shape) for grid in grids)
     results = use_mcc_batch_sharded(c1pm1i[gpi], r1pm1i[gpi], c2fg[gpi], r2fg[gpi], brd2[gpi],
                                     img1, img2, img_size, alpha0, **kwargs)
 

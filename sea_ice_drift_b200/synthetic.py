@@ -147,6 +147,12 @@ class ArrayDomain(object):
         dx, dy = x - self._fwd[0, 2], y - self._fwd[1, 2]
         return self._inv[0, 0] * dx + self._inv[0, 1] * dy, self._inv[1, 0] * dx + self._inv[1, 1] * dy
 
+    def affine_maps(self, dst_srs=None):
+        """(pixel -> destination x/y, pixel -> lon/lat) as 2 x 3 row-major matrices ``m0*col + m1*row + m2``: lets
+        ``pattern_matching`` run its post-processing on the device.  This stand-in has no projection machinery: the
+        destination SRS is lon/lat whatever ``dst_srs`` says (like ``transform_points``)."""
+        return self._fwd.copy(), self._fwd.copy()
+
     def get_corners(self):
         h, w = self.array.shape
         cols = np.array([0, 0, w, w], dtype=np.float64)

@@ -453,3 +453,34 @@ def test_tcgen05_path_equals_legacy_paths_bit_for_bit(gpu_ctx):
                 del os.environ["SID_PM_PATH"]
         assert np.array_equal(tables["tc"], tables["imma"], equal_nan=True), (s, len(angles))
         assert np.array_equal(tables["tc"], tables["dp4a"], equal_nan=True), (s, len(angles))
+
+
+def test_device_epilogue_equals_host_post_processing():
+    """remainder add, pixel -> x/y / lon/lat, u/v differences and the _fill_gpi scatter on the device
+    (sid_pm_epilogue_affine, table kept on the device) give the same seven grids, bit for bit, as the host lines that
+    restate reference pmlib.py:462-497."""
+    side = 900
+    img1 = syn.speckle_image((side, side), seed=41)
+    m = syn.rotation_matrix((side, side), 1.0)
+    m[0, 2] += 3.3
+    img2 = syn.warp_pair(img1, m, seed=41)
+    n1 = syn.ArrayDomain(img1, lon0=5.0, lat0=81.0, rot_deg=7.0)
+    n2 = syn.ArrayDomain(img2, lon0=5.0, lat0=81.0, rot_deg=7.0)
+    rng = np.random.default_rng(8)
+    kx, ky = rng.uniform(30, side - 30, 500), rng.uniform(30, side - 30, 500)
+    k2x, k2y = syn.apply_affine(m, kx, ky)
+    gx, gy = np.meshgrid(np.linspace(-20, side + 20, 23) + 0.37, np.linspace(-20, side + 20, 21) + 0.21)   # some points outside
+    lon, lat = n2.transform_points(gx, gy)
+    with contextlib.redirect_stdout(io.StringIO()):
+        dev = sid.pattern_matching(lon, lat, n1, kx, ky, n2, k2x, k2y, angles=[-3, 0, 3])
+        host = sid.pattern_matching(lon, lat, n1, kx, ky, n2, k2x, k2y, angles=[-3, 0, 3], device_epilogue=False)
+    assert np.isfinite(dev[0]).sum() > 100 and np.isnan(dev[0]).any()
+    for name, a, b in zip("u v a r h lon2 lat2".split(), dev, host):
+        assert a.shape == lon.shape and np.array_equal(a, b, equal_nan=True), name
+    # the C entry point also accepts a host table
+    ctx = _lib.default_context()
+    gpi = np.isfinite(host[2]).ravel()
+    c2pm1, r2pm1 = n2.transform_points(lon.ravel(), lat.ravel(), 1)
+    table = np.column_stack([np.arange(gpi.sum(), dtype=np.float64)] * 5)
+    grids = ctx.pm_epilogue_affine(gpi, c2pm1, r2pm1, *n2.affine_maps(), results=table)
+    assert np.array_equal(grids[2][gpi], table[:, 2]) and np.isnan(grids[2][~gpi]).all()
