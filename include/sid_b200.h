@@ -95,6 +95,18 @@ int sid_adopt_pair_device(sid_ctx *ctx,
                           uint8_t *d_img1, int rows1, int cols1, int64_t pitch1, int64_t bytes1,
                           uint8_t *d_img2, int rows2, int cols2, int64_t pitch2, int64_t bytes2);
 
+/* First guess of pattern_matching on the device (reference pmlib.py:249-324 prepare_first_guess, pmlib.py:61-77
+ * get_distance_to_nearest_keypoint; lib.py:179-201 interpolation_near): for every query point q
+ *   out_vx/out_vy  the Delaunay-linear interpolant of (vx, vy) given at the sources (sx, sy) -- what
+ *                  scipy.interpolate.griddata(method='linear') returns -- NaN outside the sources' convex hull;
+ *   out_dist       the distance to the nearest (kx, ky) point (the reference samples a full-image distance transform);
+ *   out_flag       0 ok, 1 outside the hull, 2 not resolved numerically (caller falls back to its host path).
+ * No triangulation is built: each point finds its own Delaunay triangle by pivoting (csrc/sid_fg_kernel.cuh). */
+int sid_first_guess(sid_ctx *ctx, int n_src, const double *sx, const double *sy, const double *vx, const double *vy,
+                    int n_seed, const double *kx, const double *ky,
+                    int64_t n_q, const double *qx, const double *qy,
+                    double *out_vx, double *out_vy, double *out_dist, int32_t *out_flag);
+
 /* Post-processing of pattern_matching for AFFINE geolocation (reference pmlib.py:462-497 and lib.py:408-412), on the
  * device: sub-pixel remainder c2 += c2pm1 - round(c2pm1), pixel -> destination x/y and lon/lat, u = x2 - x1,
  * v = y2 - y1, and the _fill_gpi scatter into NaN-filled grids.

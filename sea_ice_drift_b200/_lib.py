@@ -22,7 +22,7 @@ SID_HES_NORM, SID_HES_SMTH, SID_MCC_NORM = 1, 2, 4
 
 EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
-    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_upload_rows", "sid_pm_epilogue_affine", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
+    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_upload_rows", "sid_pm_epilogue_affine", "sid_first_guess", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
     "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian", "sid_knn_hamming2",
     "sid_deformation",
 ]
@@ -64,6 +64,8 @@ def load_library():
         lib.sid_adopt_pair_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                               C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64]
         lib.sid_pm_epilogue_affine.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        lib.sid_first_guess.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + \
+            [C.c_int64] + [C.c_void_p] * 6
         lib.sid_upload_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int]
         lib.sid_run.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
@@ -220,6 +222,21 @@ class Context(object):
             self._h, idx.size, idx.ctypes.data, gpi.size, c.ctypes.data, r.ctypes.data,
             None if res is None else res.ctypes.data, xy.ctypes.data, ll.ctypes.data, out.ctypes.data))
         return out
+
+    def first_guess(self, sx, sy, vx, vy, kx, ky, qx, qy):
+        """Delaunay-linear interpolation of (vx, vy) from the sources (sx, sy) onto (qx, qy) and the distance of every
+        query point to the nearest (kx, ky) point (sid_first_guess).  Returns (vx_q, vy_q, dist, flag)."""
+        f64 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+        sx, sy, vx, vy, kx, ky, qx, qy = map(f64, (sx, sy, vx, vy, kx, ky, qx, qy))
+        if not (sx.size == sy.size == vx.size == vy.size) or kx.size != ky.size or qx.size != qy.size:
+            raise ValueError("coordinate / value arrays must have matching lengths")
+        ovx, ovy, od = (np.empty(qx.size, dtype=np.float64) for _ in range(3))
+        flag = np.zeros(qx.size, dtype=np.int32)
+        self._check(self._lib.sid_first_guess(
+            self._h, sx.size, sx.ctypes.data, sy.ctypes.data, vx.ctypes.data, vy.ctypes.data, kx.size, kx.ctypes.data,
+            ky.ctypes.data, qx.size, qx.ctypes.data, qy.ctypes.data, ovx.ctypes.data, ovy.ctypes.data, od.ctypes.data,
+            flag.ctypes.data))
+        return ovx, ovy, od, flag
 
     def upload_rows(self, dst_ptr, dst_pitch, rows_array):
         """Asynchronous 2-D upload of image rows (uint8, unit column stride) to ``dst_ptr`` on the context's stream."""

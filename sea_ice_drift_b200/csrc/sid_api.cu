@@ -19,6 +19,7 @@
 #include "sid_single_kernels.cuh"
 #include "sid_knn_kernel.cuh"
 #include "sid_defor_kernel.cuh"
+#include "sid_fg_kernel.cuh"
 
 using namespace sid;
 
@@ -52,7 +53,7 @@ struct sid_ctx {
     long long pitch1 = 0, pitch2 = 0;
     bool have_pair = false;
     // per-call buffers
-    DevBuf pts, order, out, status, angles, scratch, counter, misc, tail_maps, tail_recs, epi;
+    DevBuf pts, order, out, status, angles, scratch, counter, misc, tail_maps, tail_recs, epi, fg;
     void *pin = nullptr;
     size_t pin_cap = 0;
     cudaEvent_t k_ev[2] = {};                // bracket the last fused-kernel launch (sid_last_kernel_ms)
@@ -435,7 +436,7 @@ void sid_destroy(sid_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->img1, &ctx->img2, &ctx->pts, &ctx->order, &ctx->out, &ctx->status,
-                      &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs, &ctx->epi};
+                      &ctx->angles, &ctx->scratch, &ctx->counter, &ctx->misc, &ctx->tail_maps, &ctx->tail_recs, &ctx->epi, &ctx->fg};
     for (DevBuf *b : bufs) if (b->p && b->owned) cudaFree(b->p);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -892,6 +893,109 @@ int sid_pm_epilogue_affine(sid_ctx *ctx, int64_t n_valid, const int32_t *grid_in
     ctx->launches += n_valid ? 2 : 1;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, d_out, b_out, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SID_OK;
+}
+
+// ------------------------------------------------------------------ first guess
+namespace {
+struct HostGrid {
+    std::vector<double> x, y;
+    std::vector<int> start, index;
+    double x0 = 0, y0 = 0, cell = 1;
+    int nx = 1, ny = 1;
+};
+// uniform hash grid, ~2 points per cell, points sorted by cell (counting sort)
+void build_grid(const double *px, const double *py, int n, HostGrid &g) {
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int i = 0; i < n; ++i) { xmin = std::min(xmin, px[i]); xmax = std::max(xmax, px[i]); ymin = std::min(ymin, py[i]); ymax = std::max(ymax, py[i]); }
+    if (n == 0) { xmin = ymin = 0; xmax = ymax = 1; }
+    const double w = std::max(xmax - xmin, 1.0), h = std::max(ymax - ymin, 1.0);
+    g.cell = std::max(std::sqrt(w * h * 2.0 / std::max(n, 1)), 1.0);
+    g.nx = std::min(2048, std::max(1, (int)std::ceil(w / g.cell) + 1));
+    g.ny = std::min(2048, std::max(1, (int)std::ceil(h / g.cell) + 1));
+    g.cell = std::max(g.cell, std::max(w / (g.nx - 0.5), h / (g.ny - 0.5)));
+    g.x0 = xmin; g.y0 = ymin;
+    const double inv = 1.0 / g.cell;
+    auto cell_of = [&](double v, double v0, int m) { int c = (int)std::floor((v - v0) * inv); return c < 0 ? 0 : (c >= m ? m - 1 : c); };
+    std::vector<int> cid((size_t)n);
+    g.start.assign((size_t)g.nx * g.ny + 1, 0);
+    for (int i = 0; i < n; ++i) { cid[(size_t)i] = cell_of(py[i], g.y0, g.ny) * g.nx + cell_of(px[i], g.x0, g.nx); ++g.start[(size_t)cid[(size_t)i] + 1]; }
+    for (size_t c = 0; c + 1 < g.start.size(); ++c) g.start[c + 1] += g.start[c];
+    std::vector<int> fill(g.start.begin(), g.start.end() - 1);
+    g.x.resize((size_t)n); g.y.resize((size_t)n); g.index.resize((size_t)n);
+    for (int i = 0; i < n; ++i) { const int k = fill[(size_t)cid[(size_t)i]]++; g.x[(size_t)k] = px[i]; g.y[(size_t)k] = py[i]; g.index[(size_t)k] = i; }
+}
+// convex hull (Andrew's monotone chain), counter-clockwise, collinear points dropped
+void convex_hull(const double *px, const double *py, int n, std::vector<int> &hull) {
+    std::vector<int> idx((size_t)n);
+    for (int i = 0; i < n; ++i) idx[(size_t)i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return px[a] < px[b] || (px[a] == px[b] && py[a] < py[b]); });
+    auto cross = [&](int o, int a, int b) { return (px[a] - px[o]) * (py[b] - py[o]) - (py[a] - py[o]) * (px[b] - px[o]); };
+    hull.assign((size_t)2 * n + 2, 0);
+    int k = 0;
+    for (int i = 0; i < n; ++i) { while (k >= 2 && cross(hull[(size_t)k - 2], hull[(size_t)k - 1], idx[(size_t)i]) <= 0) --k; hull[(size_t)k++] = idx[(size_t)i]; }
+    for (int i = n - 2, t = k + 1; i >= 0; --i) { while (k >= t && cross(hull[(size_t)k - 2], hull[(size_t)k - 1], idx[(size_t)i]) <= 0) --k; hull[(size_t)k++] = idx[(size_t)i]; }
+    hull.resize((size_t)std::max(0, k - 1));
+}
+}  // namespace
+
+int sid_first_guess(sid_ctx *ctx, int n_src, const double *sx, const double *sy, const double *vx, const double *vy,
+                    int n_seed, const double *kx, const double *ky, int64_t n_q, const double *qx, const double *qy,
+                    double *out_vx, double *out_vy, double *out_dist, int32_t *out_flag) {
+    if (!ctx) return SID_EINVAL;
+    if (n_src < 0 || n_seed < 0 || n_q < 0 || (n_src > 0 && (!sx || !sy || !vx || !vy)) || (n_seed > 0 && (!kx || !ky)) ||
+        (n_q > 0 && (!qx || !qy || !out_vx || !out_vy || !out_dist || !out_flag)))
+        return fail(ctx, SID_EINVAL, "bad first-guess arguments");
+    if (n_q == 0) return SID_OK;
+    CU(cudaSetDevice(ctx->device));
+    HostGrid gs, gk;
+    build_grid(sx, sy, n_src, gs);
+    build_grid(kx, ky, n_seed, gk);
+    std::vector<int> hull;
+    if (n_src >= 3) convex_hull(sx, sy, n_src, hull);
+    const int nh = (int)hull.size();
+    std::vector<double> hx((size_t)nh), hy((size_t)nh);
+    for (int i = 0; i < nh; ++i) { hx[(size_t)i] = sx[hull[(size_t)i]]; hy[(size_t)i] = sy[hull[(size_t)i]]; }
+    // one staging block: everything the kernel reads, 256-byte aligned pieces
+    struct Piece { const void *src; size_t bytes; size_t off; };
+    std::vector<Piece> pieces;
+    size_t total = 0;
+    auto add = [&](const void *p, size_t bytes) { pieces.push_back({p, bytes, total}); total += (bytes + 255) & ~(size_t)255; return pieces.size() - 1; };
+    const size_t i_sx = add(gs.x.data(), (size_t)n_src * 8), i_sy = add(gs.y.data(), (size_t)n_src * 8);
+    const size_t i_ss = add(gs.start.data(), gs.start.size() * 4), i_si = add(gs.index.data(), (size_t)n_src * 4);
+    const size_t i_vx = add(vx, (size_t)n_src * 8), i_vy = add(vy, (size_t)n_src * 8);
+    const size_t i_hx = add(hx.data(), (size_t)nh * 8), i_hy = add(hy.data(), (size_t)nh * 8), i_hi = add(hull.data(), (size_t)nh * 4);
+    const size_t i_kx = add(gk.x.data(), (size_t)n_seed * 8), i_ky = add(gk.y.data(), (size_t)n_seed * 8);
+    const size_t i_ks = add(gk.start.data(), gk.start.size() * 4), i_ki = add(gk.index.data(), (size_t)n_seed * 4);
+    const size_t i_qx = add(qx, (size_t)n_q * 8), i_qy = add(qy, (size_t)n_q * 8);
+    const size_t o_vx = total; total += ((size_t)n_q * 8 + 255) & ~(size_t)255;
+    const size_t o_vy = total; total += ((size_t)n_q * 8 + 255) & ~(size_t)255;
+    const size_t o_d = total; total += ((size_t)n_q * 8 + 255) & ~(size_t)255;
+    const size_t o_f = total; total += ((size_t)n_q * 4 + 255) & ~(size_t)255;
+    int rc = reserve(ctx, ctx->fg, total);
+    if (rc) return rc;
+    char *base = (char *)ctx->fg.p;
+    for (const Piece &pc : pieces)
+        if (pc.bytes) CU(cudaMemcpyAsync(base + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FgArgs a;
+    memset(&a, 0, sizeof a);
+    auto at = [&](size_t i) { return base + pieces[i].off; };
+    a.src.x = (const double *)at(i_sx); a.src.y = (const double *)at(i_sy); a.src.start = (const int *)at(i_ss); a.src.index = (const int *)at(i_si);
+    a.src.x0 = gs.x0; a.src.y0 = gs.y0; a.src.cell = gs.cell; a.src.inv_cell = 1.0 / gs.cell; a.src.nx = gs.nx; a.src.ny = gs.ny; a.src.n = n_src;
+    a.vx = (const double *)at(i_vx); a.vy = (const double *)at(i_vy);
+    a.hx = (const double *)at(i_hx); a.hy = (const double *)at(i_hy); a.hidx = (const int *)at(i_hi); a.nh = nh;
+    a.seed.x = (const double *)at(i_kx); a.seed.y = (const double *)at(i_ky); a.seed.start = (const int *)at(i_ks); a.seed.index = (const int *)at(i_ki);
+    a.seed.x0 = gk.x0; a.seed.y0 = gk.y0; a.seed.cell = gk.cell; a.seed.inv_cell = 1.0 / gk.cell; a.seed.nx = gk.nx; a.seed.ny = gk.ny; a.seed.n = n_seed;
+    a.nq = n_q; a.qx = (const double *)at(i_qx); a.qy = (const double *)at(i_qy);
+    a.out_vx = (double *)(base + o_vx); a.out_vy = (double *)(base + o_vy); a.out_dist = (double *)(base + o_d); a.out_flag = (int *)(base + o_f);
+    first_guess_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_vx, base + o_vx, (size_t)n_q * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_vy, base + o_vy, (size_t)n_q * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_dist, base + o_d, (size_t)n_q * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_flag, base + o_f, (size_t)n_q * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SID_OK;
 }

@@ -182,27 +182,83 @@ def get_initial_rotation(n1, n2):
     return np.degrees(np.arctan2(x1 - x0, y1 - y0)[0])
 
 
+def _device_present():
+    """True when a CUDA device (and the library) can be used for the first guess."""
+    try:
+        _lib.default_context()
+        return True
+    except Exception:
+        return False
+
+
+def _near_device(ctx, sx, sy, vx, vy, qx, qy, seeds=None):
+    """interpolation_near(method='linear') (and optionally the nearest-seed distance) through sid_first_guess.
+    Returns (vx_q, vy_q, dist, resolved): ``resolved`` False when some point could not be decided numerically."""
+    kx, ky = seeds if seeds is not None else (np.zeros(0), np.zeros(0))
+    ovx, ovy, dist, flag = ctx.first_guess(sx, sy, vx, vy, kx, ky, qx, qy)
+    shape = np.shape(qx)
+    return ovx.reshape(shape), ovy.reshape(shape), dist.reshape(shape), not np.any(flag == 2)
+
+
 def prepare_first_guess(c2pm1, r2pm1, n1, c1, r1, n2, c2, r2, img_size,
                         min_fg_pts=5, min_border=20, max_border=50, old_border=True, **kwargs):
     """First-guess position on image 2 and search radius for every grid point
     (reference pmlib.py:249-324): Delaunay-linear interpolation of the feature
     tracking vectors with a polynomial fallback outside their hull; the radius is
-    the distance to the nearest keypoint clamped to [min_border, max_border]."""
+    the distance to the nearest keypoint clamped to [min_border, max_border].
+
+    ``first_guess='device'`` (the default where a CUDA device is present) evaluates the Delaunay-linear interpolant and
+    the nearest-keypoint distances on the GPU without building a triangulation (``sid_first_guess``: every grid point
+    finds its own Delaunay triangle by pivoting); ``first_guess='host'`` is the SciPy path (one Qhull triangulation
+    shared by both value sets, KD-tree distances) -- also taken for ``method != 'linear'`` and for any point the
+    device could not resolve numerically.  Both give the same ``c2fg, r2fg, border``."""
     n2_shape = n2.shape()
     lon1, lat1 = n1.transform_points(c1, r1)
     c1n2, r1n2 = n2.transform_points(lon1, lat1, 1)
     c2p2, r2p2 = np.round(interpolation_poly(c1n2, r1n2, c2, r2, c2pm1, r2pm1, **kwargs))
-    c2fg, r2fg = np.round(interpolation_near(c1n2, r1n2, c2, r2, c2pm1, r2pm1, **kwargs))
-    if old_border:
-        border = np.zeros(c2pm1.size) + max_border
+    mode = kwargs.get('first_guess')
+    if mode is None:
+        mode = 'device' if (kwargs.get('method', 'linear') == 'linear' and len(np.atleast_1d(c1)) >= 3
+                            and _device_present()) else 'host'
+    done = False
+    if mode == 'device':
+        ctx = _ctx(kwargs)
+        c2pm1 = np.asarray(c2pm1, dtype=np.float64)
+        r2pm1 = np.asarray(r2pm1, dtype=np.float64)
         inside = ((c2pm1 >= 0) * (c2pm1 < n2_shape[1]) * (r2pm1 >= 0) * (r2pm1 < n2_shape[0]))
-        border[inside] = _distance_at(c2, r2,
-                                      np.round(c2pm1[inside]).astype(np.int16),
-                                      np.round(r2pm1[inside]).astype(np.int16))
-    else:
-        c2tst, r2tst = interpolation_poly(c1n2, r1n2, c2, r2, c1n2, r1n2, **kwargs)
-        c2dif, r2dif = interpolation_near(c1n2, r1n2, c2 - c2tst, r2 - r2tst, c2pm1, r2pm1, **kwargs)
-        border = np.hypot(c2dif, r2dif)
+        seeds = (np.uint16(c2).astype(np.float64), np.uint16(r2).astype(np.float64))
+        integer_grid = np.array_equal(np.round(c2pm1), c2pm1) and np.array_equal(np.round(r2pm1), r2pm1)
+        if old_border:
+            vx, vy, dist, ok = _near_device(ctx, c1n2, r1n2, c2, r2, c2pm1, r2pm1, seeds if integer_grid else None)
+            if ok and not integer_grid:      # the reference samples the distance image at the ROUNDED grid positions
+                dist = _near_device(ctx, np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0),
+                                    np.round(c2pm1).astype(np.int16).astype(np.float64),
+                                    np.round(r2pm1).astype(np.int16).astype(np.float64), seeds)[2]
+            if ok:
+                c2fg, r2fg = np.round(vx), np.round(vy)
+                border = np.zeros(c2pm1.size) + max_border
+                border[inside.ravel()] = dist.ravel()[inside.ravel()]
+                done = True
+        else:
+            c2tst, r2tst = interpolation_poly(c1n2, r1n2, c2, r2, c1n2, r1n2, **kwargs)
+            vx, vy, _, ok = _near_device(ctx, c1n2, r1n2, c2, r2, c2pm1, r2pm1)
+            dx, dy, _, ok2 = _near_device(ctx, c1n2, r1n2, c2 - c2tst, r2 - r2tst, c2pm1, r2pm1)
+            if ok and ok2:
+                c2fg, r2fg = np.round(vx), np.round(vy)
+                border = np.hypot(dx, dy)
+                done = True
+    if not done:
+        c2fg, r2fg = np.round(interpolation_near(c1n2, r1n2, c2, r2, c2pm1, r2pm1, **kwargs))
+        if old_border:
+            border = np.zeros(c2pm1.size) + max_border
+            inside = ((c2pm1 >= 0) * (c2pm1 < n2_shape[1]) * (r2pm1 >= 0) * (r2pm1 < n2_shape[0]))
+            border[inside] = _distance_at(c2, r2,
+                                          np.round(c2pm1[inside]).astype(np.int16),
+                                          np.round(r2pm1[inside]).astype(np.int16))
+        else:
+            c2tst, r2tst = interpolation_poly(c1n2, r1n2, c2, r2, c1n2, r1n2, **kwargs)
+            c2dif, r2dif = interpolation_near(c1n2, r1n2, c2 - c2tst, r2 - r2tst, c2pm1, r2pm1, **kwargs)
+            border = np.hypot(c2dif, r2dif)
     border[border < min_border] = min_border
     border[border > max_border] = max_border
     outside_hull = np.isnan(c2fg)

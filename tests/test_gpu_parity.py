@@ -484,3 +484,68 @@ def test_device_epilogue_equals_host_post_processing():
     table = np.column_stack([np.arange(gpi.sum(), dtype=np.float64)] * 5)
     grids = ctx.pm_epilogue_affine(gpi, c2pm1, r2pm1, *n2.affine_maps(), results=table)
     assert np.array_equal(grids[2][gpi], table[:, 2]) and np.isnan(grids[2][~gpi]).all()
+
+
+def _fg_case(side, n_kp, grid, seed, integer_keypoints=False):
+    rng = np.random.default_rng(seed)
+    img = np.zeros((side, side), np.uint8)
+    n1, n2 = syn.ArrayDomain(img), syn.ArrayDomain(img)
+    m = syn.rotation_matrix((side, side), 1.5)
+    m[0, 2] += 7.0
+    kx, ky = rng.uniform(40, side - 40, n_kp), rng.uniform(40, side - 40, n_kp)
+    if integer_keypoints:
+        kx, ky = np.round(kx), np.round(ky)
+    k2x, k2y = syn.apply_affine(m, kx, ky)
+    k2x, k2y = k2x + rng.normal(0, 0.8, n_kp), k2y + rng.normal(0, 0.8, n_kp)
+    gx, gy = np.meshgrid(np.linspace(-30, side + 30, grid), np.linspace(-30, side + 30, grid))   # some points outside the hull / image
+    return n1, n2, kx, ky, k2x, k2y, np.round(gx.ravel()), np.round(gy.ravel())
+
+
+@pytest.mark.parametrize("old_border", [True, False])
+def test_first_guess_on_device_equals_host_path(old_border):
+    """sid_first_guess (Delaunay-free local interpolation + exact nearest-keypoint distance) gives the
+    same c2fg, r2fg, border as the SciPy path (Qhull triangulation + KD-tree) that equals the reference."""
+    for side, n_kp, grid, seed in ((700, 400, 30, 1), (3000, 6000, 70, 2)):
+        n1, n2, kx, ky, k2x, k2y, gx, gy = _fg_case(side, n_kp, grid, seed)
+        dev = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, old_border=old_border, first_guess='device')
+        host = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, old_border=old_border, first_guess='host')
+        for name, a, b in zip(("c2fg", "r2fg", "border"), dev, host):
+            assert np.array_equal(a, b, equal_nan=True), (name, side, int((a != b).sum()))
+
+
+def test_first_guess_on_device_ew_size_and_interpolant_values():
+    """EW size (10400 x 10400, 50 000 keypoints, 200 x 200 grid): identical outputs, and the raw interpolant agrees with
+    scipy's LinearNDInterpolator to rounding error; timing printed for the record."""
+    import time
+    from scipy.interpolate import LinearNDInterpolator
+    n1, n2, kx, ky, k2x, k2y, gx, gy = _fg_case(10400, 50000, 200, 3)
+    sid.prepare_first_guess(gx[:10], gy[:10], n1, kx, ky, n2, k2x, k2y, 35, first_guess='device')       # warm-up
+    t0 = time.perf_counter()
+    dev = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, first_guess='device')
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    host = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, first_guess='host')
+    t_host = time.perf_counter() - t0
+    print("prepare_first_guess EW size: device %.1f ms, host %.1f ms" % (1e3 * t_dev, 1e3 * t_host))
+    for name, a, b in zip(("c2fg", "r2fg", "border"), dev, host):
+        assert np.array_equal(a, b, equal_nan=True), (name, int((a != b).sum()))
+    ctx = _lib.default_context()
+    vx, vy, dist, flag = ctx.first_guess(kx, ky, k2x, k2y, np.uint16(k2x), np.uint16(k2y), gx, gy)
+    ref = LinearNDInterpolator(np.column_stack([ky, kx]), np.column_stack([k2x, k2y]))(np.column_stack([gy, gx]))
+    inside = ~np.isnan(ref[:, 0])
+    assert np.array_equal(flag == 1, ~inside) and not np.any(flag == 2)
+    assert np.abs(vx[inside] - ref[inside, 0]).max() < 1e-7 and np.abs(vy[inside] - ref[inside, 1]).max() < 1e-7
+    assert t_dev < 0.25 * t_host
+
+
+def test_first_guess_integer_keypoints_cocircular_degeneracies():
+    """ORB keypoints of pyramid level 0 sit on integer pixels, so four of them can be cocircular and the Delaunay
+    triangulation is then not unique (Qhull's choice is arbitrary too): the device result must still be a valid
+    Delaunay interpolant -- equal to the SciPy path except at grid points inside such degenerate cells."""
+    n1, n2, kx, ky, k2x, k2y, gx, gy = _fg_case(1200, 3000, 60, 4, integer_keypoints=True)
+    dev = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, first_guess='device')
+    host = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, first_guess='host')
+    assert np.array_equal(dev[2], host[2])                                   # distances are exact either way
+    differ = (dev[0] != host[0]) | (dev[1] != host[1])
+    assert differ.mean() < 0.02, differ.mean()
+    assert np.abs(dev[0] - host[0]).max() <= 3 and np.abs(dev[1] - host[1]).max() <= 3
