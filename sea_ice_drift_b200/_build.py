@@ -28,7 +28,7 @@ def is_stale():
 
 def build(force=False, verbose=False, out=None, extra=()):
     """``out`` / ``extra``: build an experimental variant next to the product library, e.g.
-    ``build(force=True, out='/tmp/libsid_kstd.so', extra=['-DSID_IMMA_KSTD'])`` for an A/B run."""
+    ``build(force=True, out='/tmp/libsid_variant.so', extra=['-DSOME_SWITCH'])`` for an A/B run."""
     if not force and not is_stale() and out is None:
         return LIB
     cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \

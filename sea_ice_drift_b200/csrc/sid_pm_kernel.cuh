@@ -84,11 +84,7 @@ struct PmArgs {
 __host__ __device__ inline int pm_window_pitch_words(int W, bool imma = false) {
     if (imma) {
         int w = (W + 4 + 3) / 4;
-#ifdef SID_IMMA_KSTD                      // candidate layout: pitch == 4 (mod 8) words, conflict-free scalar A loads
-        while ((w & 7) != 4) ++w;
-#else                                     // pitch == 8 (mod 16) words
-        while ((w & 15) != 8) ++w;
-#endif
+        while ((w & 15) != 8) ++w;             // pitch == 8 (mod 16) words
         return w;
     }
     int n16 = (W + 4 + 15) / 16;          // 16-byte units, with room for the shifted tail
@@ -259,17 +255,8 @@ __device__ __forceinline__ void pm_tiles_imma(const uint32_t *__restrict__ win32
     const int g = lane >> 2, tig = lane & 3;
     const int nxg = (RW + ab + 23) / 24;               // tiles over shifted columns x' = x + ab (see pm_tiles)
     const int ntiles = ((RH + 15) >> 4) * nxg;
-#ifdef SID_IMMA_KSTD
-    // Candidate K mapping (not built by default; checked on the CPU by tests/imma_layout_emulation.py): hardware K slot k
-    // holds window byte k, i.e. a lane's A words are tig and tig+4 -- with a pitch == 4 (mod 8) words the 8 rows x 4 lanes
-    // of a scalar load hit 32 distinct banks (the permuted mapping below always takes 2 wavefronts).  Its B words are two
-    // unaligned words 16 bytes apart: bytes (8 + 4*tig - g) and +16 of the padded template row.
-    const int ob = 8 + 4 * tig - g;
-    constexpr int A_LANE = 1, A_HI = 4, B_HI = 4;
-#else
     const int ob = 8 + 8 * tig - g;               // byte offset of this lane's B bytes inside a padded template row
     constexpr int A_LANE = 2, A_HI = 1, B_HI = 1;
-#endif
     const int bw = ob >> 2, bsh = (ob & 3) * 8;
     unsigned long long key[NBA];
 #pragma unroll
