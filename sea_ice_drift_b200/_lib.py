@@ -41,9 +41,11 @@ def load_library():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
-        if _build.is_stale():
-            path = _build.build()
+        path = os.environ.get("SID_LIBRARY")          # an experimental build for A/B runs (scratch/ab_build.sh)
+        if not path:
+            path = _build.LIB
+            if _build.is_stale():
+                path = _build.build()
         lib = C.CDLL(path)
         lib.sid_version.restype = C.c_char_p
         lib.sid_last_error.restype = C.c_char_p

@@ -36,7 +36,8 @@ struct FgArgs {
     long long nq;
     const double *qx, *qy; // query points
     double *out_vx, *out_vy, *out_dist;
-    int *out_flag;         // 0 ok, 1 outside the hull (NaN), 2 pivot limit reached (caller falls back to the host)
+    int *out_flag;         // 0 ok, 1 outside the hull (NaN), 2 not resolved numerically, 3 ok but a further keypoint lies ON the
+                           // circumcircle: the Delaunay triangulation is not unique there (Qhull's choice may differ)
 };
 
 __device__ __forceinline__ double fg_orient(double ax, double ay, double bx, double by, double cx, double cy) {
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(128) first_guess_kernel(const FgArgs a) {
         const int y_lo = fg_cell(oy - rad, g.y0, g.inv_cell, g.ny), y_hi = fg_cell(oy + rad, g.y0, g.inv_cell, g.ny);
         double deepest = 0.0, px = 0.0, py = 0.0;
         int ip = -1;
+        bool on_circle = false;
         // scan the cells under the circle in rings around q's own cell and pivot on the deepest violator of the FIRST ring
         // that holds one: points near q shrink a large circle quickly (a starting triangle at the hull can span the whole
         // point set), and only the final, empty circle is scanned completely
@@ -195,13 +197,19 @@ __global__ void __launch_bounds__(128) first_guess_kernel(const FgArgs a) {
                     for (int k = g.start[c]; k < g.start[c + 1]; ++k) {
                         const int id = g.index[k];
                         if (id == ia || id == ib || id == ic) continue;
-                        const double v = fg_incircle(ax, ay, bx, by, cx_, cy_, g.x[k], g.y[k]);
-                        if (v > deepest) { deepest = v; px = g.x[k]; py = g.y[k]; ip = id; }
+                        const double dxk = g.x[k], dyk = g.y[k];
+                        const double v = fg_incircle(ax, ay, bx, by, cx_, cy_, dxk, dyk);
+                        // |v| at rounding-error level of its own terms (exactly 0 for cocircular integer pixels): not unique
+                        const double sa = (ax - dxk) * (ax - dxk) + (ay - dyk) * (ay - dyk), sb = (bx - dxk) * (bx - dxk) + (by - dyk) * (by - dyk),
+                                     sc = (cx_ - dxk) * (cx_ - dxk) + (cy_ - dyk) * (cy_ - dyk);
+                        const double tol = 4e-14 * (sa + sb + sc) * (sa + sb + sc);
+                        if (v > tol) { if (v > deepest) { deepest = v; px = dxk; py = dyk; ip = id; } }
+                        else if (v >= -tol) on_circle = true;
                     }
                 }
             }
         }
-        if (ip < 0) break;                                       // empty circumcircle: a Delaunay triangle
+        if (ip < 0) { if (on_circle) flag = 3; break; }          // empty circumcircle: a Delaunay triangle
         // the new triangle has the deepest point p as a vertex and still contains q
         if (fg_contains(px, py, ax, ay, bx, by, qx, qy)) { cx_ = px; cy_ = py; ic = ip; }
         else if (fg_contains(px, py, bx, by, cx_, cy_, qx, qy)) { ax = px; ay = py; ia = ip; }

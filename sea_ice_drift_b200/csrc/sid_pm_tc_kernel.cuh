@@ -32,6 +32,9 @@
 namespace sid {
 
 constexpr int TC_THREADS = 256;
+#ifndef SID_TC_OLD_TPL_LAYOUT
+#define SID_TC_OLD_TPL_LAYOUT 0        // A/B switch: 1 = round-2 first template layout (copy stride 20 words, angle skew 4)
+#endif
 
 // Launch-uniform geometry of the tcgen05 path, computed on the host (pm_tc_geometry).
 struct PmTcCfg {
@@ -71,9 +74,14 @@ inline bool pm_tc_geometry(int s, int Rmax, int Wmax, int n_angles, PmTcCfg &g) 
     const int bandw = (3 + (xspan - 1) + (s - 1)) / 4 + 1;          // K words between a warp's first and last non-zero byte
     g.nb8 = (bandw + 7) / 8;
     g.ctlw = (3 + xspan - 1) / 4;
+    // Bank layout of the template area: a warp's 32 lanes (11-12 x positions x 3 angles) read, per band word, from 12
+    // (angle, copy) rows at 3-4 consecutive word offsets each.  Copy stride == 24 (mod 32) words puts the four copies on
+    // banks 0 / 24 / 16 / 8 and an angle skew of 3 words interleaves the angles between them (the first layout, stride
+    // 20 for both, made 3-way conflicts of every band load: 51 % of the kernel's shared wavefronts were replays).
     int tpw = g.ctlw + 8 * g.nb8;
-    tpw = (tpw + 3) & ~3;
-    if ((tpw & 7) == 0) tpw += 4;                                   // copies 0..3 start on different banks
+    int askew = 16;
+    if (tpw <= 24 && !SID_TC_OLD_TPL_LAYOUT) { tpw = 24; askew = 12; }
+    else { tpw = (tpw + 3) & ~3; if ((tpw & 7) == 0) tpw += 4; }
     g.tpw = tpw;
     const int max_cw0 = (96 / g.nab + 15) >> 2;                     // first band word of the last warp, worst offset
     int slotc = max_cw0 + 8 * g.nb8;
@@ -100,7 +108,7 @@ inline bool pm_tc_geometry(int s, int Rmax, int Wmax, int n_angles, PmTcCfg &g) 
     if (g.npanels < g.np_load) g.npanels = g.np_load;
     g.load_rows = Wmax;
     g.win_bytes = g.npanels * g.wrows * 16;
-    g.tang = s * 4 * g.tpw * 4 + 16;
+    g.tang = s * 4 * g.tpw * 4 + askew;
     // behind the last angle: a row of zeros (dead lanes), a row of ones and a row of 255s (window sums), 4 copies each
     g.tpl_bytes = (g.nab * g.tang + 12 * g.tpw * 4 + 127) & ~127;
     g.n16hmax = (Wmax + 15) & ~15;

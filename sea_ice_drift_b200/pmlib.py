@@ -193,11 +193,12 @@ def _device_present():
 
 def _near_device(ctx, sx, sy, vx, vy, qx, qy, seeds=None):
     """interpolation_near(method='linear') (and optionally the nearest-seed distance) through sid_first_guess.
-    Returns (vx_q, vy_q, dist, resolved): ``resolved`` False when some point could not be decided numerically."""
+    Returns (vx_q, vy_q, dist, resolved, unique): ``resolved`` False when some point could not be decided numerically,
+    ``unique`` False when some grid point lies in a cell of cocircular keypoints (triangulation not unique)."""
     kx, ky = seeds if seeds is not None else (np.zeros(0), np.zeros(0))
     ovx, ovy, dist, flag = ctx.first_guess(sx, sy, vx, vy, kx, ky, qx, qy)
     shape = np.shape(qx)
-    return ovx.reshape(shape), ovy.reshape(shape), dist.reshape(shape), not np.any(flag == 2)
+    return ovx.reshape(shape), ovy.reshape(shape), dist.reshape(shape), not np.any(flag == 2), not np.any(flag == 3)
 
 
 def prepare_first_guess(c2pm1, r2pm1, n1, c1, r1, n2, c2, r2, img_size,
@@ -207,21 +208,24 @@ def prepare_first_guess(c2pm1, r2pm1, n1, c1, r1, n2, c2, r2, img_size,
     tracking vectors with a polynomial fallback outside their hull; the radius is
     the distance to the nearest keypoint clamped to [min_border, max_border].
 
-    ``first_guess='device'`` (the default where a CUDA device is present) evaluates the Delaunay-linear interpolant and
+    ``first_guess='auto'`` (the default where a CUDA device is present) evaluates the Delaunay-linear interpolant and
     the nearest-keypoint distances on the GPU without building a triangulation (``sid_first_guess``: every grid point
-    finds its own Delaunay triangle by pivoting); ``first_guess='host'`` is the SciPy path (one Qhull triangulation
-    shared by both value sets, KD-tree distances) -- also taken for ``method != 'linear'`` and for any point the
-    device could not resolve numerically.  Both give the same ``c2fg, r2fg, border``."""
+    finds its own Delaunay triangle by pivoting) and returns that when the result is unique -- then it equals the SciPy /
+    reference values.  Where four keypoints are cocircular (integer pixel coordinates, e.g. ORB keypoints under an
+    identity geolocation) the Delaunay triangulation is not unique and Qhull's arbitrary choice may differ: ``'auto'``
+    then takes the SciPy path so that the result is always the reference's; ``first_guess='device'`` keeps the (equally
+    valid) device result.  ``first_guess='host'`` is the SciPy path (one Qhull triangulation shared by both value sets,
+    KD-tree distances), also taken for ``method != 'linear'``."""
     n2_shape = n2.shape()
     lon1, lat1 = n1.transform_points(c1, r1)
     c1n2, r1n2 = n2.transform_points(lon1, lat1, 1)
     c2p2, r2p2 = np.round(interpolation_poly(c1n2, r1n2, c2, r2, c2pm1, r2pm1, **kwargs))
     mode = kwargs.get('first_guess')
     if mode is None:
-        mode = 'device' if (kwargs.get('method', 'linear') == 'linear' and len(np.atleast_1d(c1)) >= 3
-                            and _device_present()) else 'host'
+        mode = 'auto' if (kwargs.get('method', 'linear') == 'linear' and len(np.atleast_1d(c1)) >= 3
+                          and _device_present()) else 'host'
     done = False
-    if mode == 'device':
+    if mode in ('device', 'auto'):
         ctx = _ctx(kwargs)
         c2pm1 = np.asarray(c2pm1, dtype=np.float64)
         r2pm1 = np.asarray(r2pm1, dtype=np.float64)
@@ -229,7 +233,8 @@ def prepare_first_guess(c2pm1, r2pm1, n1, c1, r1, n2, c2, r2, img_size,
         seeds = (np.uint16(c2).astype(np.float64), np.uint16(r2).astype(np.float64))
         integer_grid = np.array_equal(np.round(c2pm1), c2pm1) and np.array_equal(np.round(r2pm1), r2pm1)
         if old_border:
-            vx, vy, dist, ok = _near_device(ctx, c1n2, r1n2, c2, r2, c2pm1, r2pm1, seeds if integer_grid else None)
+            vx, vy, dist, ok, unique = _near_device(ctx, c1n2, r1n2, c2, r2, c2pm1, r2pm1, seeds if integer_grid else None)
+            ok = ok and (unique or mode == 'device')
             if ok and not integer_grid:      # the reference samples the distance image at the ROUNDED grid positions
                 dist = _near_device(ctx, np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0),
                                     np.round(c2pm1).astype(np.int16).astype(np.float64),
@@ -241,9 +246,9 @@ def prepare_first_guess(c2pm1, r2pm1, n1, c1, r1, n2, c2, r2, img_size,
                 done = True
         else:
             c2tst, r2tst = interpolation_poly(c1n2, r1n2, c2, r2, c1n2, r1n2, **kwargs)
-            vx, vy, _, ok = _near_device(ctx, c1n2, r1n2, c2, r2, c2pm1, r2pm1)
-            dx, dy, _, ok2 = _near_device(ctx, c1n2, r1n2, c2 - c2tst, r2 - r2tst, c2pm1, r2pm1)
-            if ok and ok2:
+            vx, vy, _, ok, unique = _near_device(ctx, c1n2, r1n2, c2, r2, c2pm1, r2pm1)
+            dx, dy, _, ok2, _ = _near_device(ctx, c1n2, r1n2, c2 - c2tst, r2 - r2tst, c2pm1, r2pm1)
+            if ok and ok2 and (unique or mode == 'device'):
                 c2fg, r2fg = np.round(vx), np.round(vy)
                 border = np.hypot(dx, dy)
                 done = True

@@ -533,7 +533,7 @@ def test_first_guess_on_device_ew_size_and_interpolant_values():
     vx, vy, dist, flag = ctx.first_guess(kx, ky, k2x, k2y, np.uint16(k2x), np.uint16(k2y), gx, gy)
     ref = LinearNDInterpolator(np.column_stack([ky, kx]), np.column_stack([k2x, k2y]))(np.column_stack([gy, gx]))
     inside = ~np.isnan(ref[:, 0])
-    assert np.array_equal(flag == 1, ~inside) and not np.any(flag == 2)
+    assert np.array_equal(flag == 1, ~inside) and not np.any(flag >= 2)             # resolved and unique
     assert np.abs(vx[inside] - ref[inside, 0]).max() < 1e-7 and np.abs(vy[inside] - ref[inside, 1]).max() < 1e-7
     assert t_dev < 0.25 * t_host
 
@@ -545,6 +545,11 @@ def test_first_guess_integer_keypoints_cocircular_degeneracies():
     n1, n2, kx, ky, k2x, k2y, gx, gy = _fg_case(1200, 3000, 60, 4, integer_keypoints=True)
     dev = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, first_guess='device')
     host = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35, first_guess='host')
+    auto = sid.prepare_first_guess(gx, gy, n1, kx, ky, n2, k2x, k2y, 35)       # default: detects the ambiguity, SciPy decides
+    for a, b in zip(auto, host):
+        assert np.array_equal(a, b, equal_nan=True)
+    flag = _lib.default_context().first_guess(kx, ky, k2x, k2y, kx, ky, gx, gy)[3]
+    assert (flag == 3).any() and not (flag == 2).any()
     assert np.array_equal(dev[2], host[2])                                   # distances are exact either way
     differ = (dev[0] != host[0]) | (dev[1] != host[1])
     assert differ.mean() < 0.02, differ.mean()
