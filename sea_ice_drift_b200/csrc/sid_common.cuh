@@ -266,6 +266,42 @@ __device__ __forceinline__ double ncc_finish(double num, double t) {
     if (an < __dmul_rn(t, 1.125)) return num > 0.0 ? 1.0 : -1.0;
     return 0.0;
 }
+// Four NCC values at once, branch-free on the common path so that the four FP64 division chains interleave (the IEEE
+// software division has a branch to its slow path after every quotient, which serialises consecutive divisions).
+// Quotient: Newton-refined reciprocal -> within ~1 ulp(double) of num/t; its float32 rounding equals the float32 rounding
+// of the correctly rounded double unless a float32 rounding boundary (mantissa bits below float32 = 1000...0) lies
+// within a few double ulps; those (~1 in 2^24), tiny divisors and tiny quotients are redone with the IEEE division.
+// Result bit for bit == (float)ncc_finish(num, t).
+__device__ __forceinline__ void ncc_finish4(const double (&num)[4], const double (&t)[4], float (&v)[4]) {
+    double r[4], q[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[c]) : "d"(t[c]));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { const double e = fma(-t[c], r[c], 1.0); r[c] = fma(r[c], e, r[c]); }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { const double e = fma(-t[c], r[c], 1.0); r[c] = fma(r[c], e, r[c]); }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) q[c] = num[c] * r[c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) q[c] = fma(r[c], fma(-t[c], q[c], num[c]), q[c]);
+    bool redo = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double an = fabs(num[c]);
+        const unsigned long long low = (unsigned long long)__double_as_longlong(q[c]) & 0x1fffffffull;
+        const unsigned long long d = low > 0x10000000ull ? low - 0x10000000ull : 0x10000000ull - low;
+        const bool inside = an < t[c];
+        const bool fast_ok = d > 16ull && t[c] > 1e-280 && fabs(q[c]) > 1e-30;
+        redo = redo || (inside && !fast_ok);
+        const float unit = an < __dmul_rn(t[c], 1.125) ? (num[c] > 0.0 ? 1.0f : -1.0f) : 0.0f;
+        v[c] = inside ? __double2float_rn(q[c]) : unit;
+    }
+    if (redo) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = __double2float_rn(ncc_finish(num[c], t[c]));
+    }
+}
+
 __device__ __noinline__ Ncc3 ncc_value_call3(int c0, int c1, int c2, uint32_t wsum, double wden,
                                              double m0, double n0, double m1, double n1, double m2, double n2) {
     const double ws = (double)wsum;

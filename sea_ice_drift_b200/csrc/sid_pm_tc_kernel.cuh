@@ -237,10 +237,11 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
             S.point = S.next;
             const long long pi0 = (long long)S.point;
             if (pi0 < a.n) {
-                S.next = atomicAdd(a.counter, 1u);
-                // the point's window rectangle, once for the whole CTA
+                // issue order matters here (255 threads wait at the barrier below): the point's loads first, then the
+                // work-stealing atomic, so that the two global round trips overlap instead of adding up
                 const long long pt0 = a.order ? (long long)a.order[pi0] : pi0;
                 const double c1 = a.c1[pt0], r1 = a.r1[pt0], c2 = a.c2fg[pt0], r2 = a.r2fg[pt0], brd = a.border[pt0];
+                const unsigned int nxt = atomicAdd(a.counter, 1u);
                 long long x0, y0; int W, H;
                 bool ok = pm_window_rect(a, c1, r1, c2, r2, brd, x0, y0, W, H);
                 const int RH0 = H - s + 1, RW0 = W - s + 1;
@@ -248,6 +249,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                              W + (int)(x0 & 15) <= g.np_load * 16 && RH0 <= g.n16max;
                 P.c1 = c1; P.r1 = r1; P.c2 = c2; P.r2 = r2; P.pt = pt0;
                 P.x0 = (int)x0; P.y0 = (int)y0; P.W = W; P.H = H; P.ok = ok ? 1 : 0;
+                S.next = nxt;
             }
         }
         __syncthreads();
@@ -690,6 +692,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                             }
                         }
                         if (live) {
+#ifdef SID_TC_SERIAL_NCC
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
                                 const int y = c0 + c;
@@ -704,6 +707,31 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                                     if (v > bv) { bv = v; bidx = idx; }
                                 }
                             }
+#else
+                            // two batches of four outputs: the FP64 chains of a batch are independent and interleave
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                double num[4], tt[4];
+                                float v[4];
+                                int idx4[4];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const int y = min(c0 + 4 * h + c, RH - 1);          // rows past the map repeat the last row (discarded below)
+                                    idx4[c] = y * RW + x;
+                                    num[c] = __dsub_rn((double)(int)acc[4 * h + c], __dmul_rn((double)wsum[idx4[c]], t_mean));
+                                    tt[c] = __dmul_rn(wden[idx4[c]], t_norm);
+                                }
+                                ncc_finish4(num, tt, v);
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    if (c0 + 4 * h + c < RH) {
+                                        const float vv = t_flat ? 1.0f : v[c];
+                                        my_map[idx4[c]] = vv;
+                                        if (vv > bv) { bv = vv; bidx = idx4[c]; }
+                                    }
+                                }
+                            }
+#endif
                         }
                     }
                     if (bidx >= 0) {
