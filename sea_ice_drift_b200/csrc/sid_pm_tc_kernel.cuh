@@ -56,6 +56,7 @@ struct PmTcCfg {
     int tpw;        // words per template-row copy
     int tang;       // bytes per angle in the template area
     int win_bytes, tpl_bytes;
+    unsigned par_mask;  // bit b: slot barrier b completes an ODD number of phases per tile (its parity flips from tile to tile)
     // window sums on the tensor cores (set by the host when shared memory / tensor memory allow it)
     int mma_sums;   // 1: horizontal box sums of v and v^2 by a ones-Toeplitz MMA, vertical sums from TMEM rows
     int n16hmax;    // accumulator width of those MMAs: window rows rounded up to 16
@@ -111,6 +112,9 @@ inline bool pm_tc_geometry(int s, int Rmax, int Wmax, int n_angles, PmTcCfg &g) 
     g.tang = s * 4 * g.tpw * 4 + askew;
     // behind the last angle: a row of zeros (dead lanes), a row of ones and a row of 255s (window sums), 4 copies each
     g.tpl_bytes = (g.nab * g.tang + 12 * g.tpw * 4 + 127) & ~127;
+    g.par_mask = 0;
+    for (int b = 0; b < 2 * g.nslot; ++b)            // rows b, b + 2 nslot, ... of the s template rows commit to barrier b
+        if (b < s && (((s - b + 2 * g.nslot - 1) / (2 * g.nslot)) & 1)) g.par_mask |= 1u << b;
     g.n16hmax = (Wmax + 15) & ~15;
     g.mma_sums = 0; g.sq_off = 0; g.wsq_off = 0;
     return true;
@@ -657,8 +661,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
                     }
                 }
                 if (lane == 0 && wiw < g.nissue) tc_commit(&done_bar[wg]);
-                for (int b = 0; b < 2 * g.nslot; ++b)            // completions this tile added to each slot barrier
-                    if (b < s) slot_par ^= (unsigned)(((s - b + 2 * g.nslot - 1) / (2 * g.nslot)) & 1) << b;
+                slot_par ^= g.par_mask;                          // completions this tile added to each slot barrier (host-computed)
                 mbar_wait(&done_bar[0], done_phase);
                 mbar_wait(&done_bar[1], done_phase);
                 done_phase ^= 1u;
