@@ -16,6 +16,7 @@
 #include "sid_common.cuh"
 #include "sid_pm_kernel.cuh"
 #include "sid_pm_tc_kernel.cuh"
+#include "sid_pm_ws_kernel.cuh"
 #include "sid_single_kernels.cuh"
 #include "sid_knn_kernel.cuh"
 #include "sid_defor_kernel.cuh"
@@ -24,6 +25,9 @@
 using namespace sid;
 
 namespace {
+#ifndef SID_WS_DEFAULT
+#define SID_WS_DEFAULT 0
+#endif
 
 constexpr size_t IMG_TAIL_SLACK = 4096;   // bytes readable past the last image row
 
@@ -207,6 +211,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     // (SID_PM_PATH=dp4a); all three give bit-identical results
     const char *path_env = getenv("SID_PM_PATH");
     const bool want_tc = !path_env || strcmp(path_env, "tc") == 0;
+    const bool want_ws = path_env ? strcmp(path_env, "ws") == 0 : SID_WS_DEFAULT != 0;
     const bool imma = !(path_env && strcmp(path_env, "dp4a") == 0);
     const bool smth = (flags & SID_HES_SMTH) != 0;
     // Split tail: peak statistics in a second, light kernel when the result map fits its shared memory
@@ -218,6 +223,47 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     PmTcCfg tg;
     memset(&tg, 0, sizeof tg);
     bool use_tc = false;
+    // warp-specialised pipeline kernel (sid_pm_ws_kernel.cuh): small result maps (radius <= 24), needs the split tail
+    PmWsCfg wg;
+    memset(&wg, 0, sizeof wg);
+    bool use_ws = false;
+    if (want_ws && split_tail && pm_ws_geometry(s, Rmax, Wmax, n_angles, a.max_rr, wg) &&
+        (size_t)wg.smem_bytes + 8192 <= (size_t)ctx->max_smem_optin && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows))
+        use_ws = true;
+    if (use_ws) {
+        a.tma = 1; a.ab = wg.nab;
+        int rc = reserve(ctx, ctx->counter, 256);
+        if (rc) return rc;
+        a.counter = (unsigned int *)ctx->counter.p + 16 * slot;
+        CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+        a.split_tail = 1;
+        const size_t cap_n = (size_t)std::max<long long>(n + tail_off, ctx->tail_hint_n);
+        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.max_rr * sizeof(float)))) return rc;
+        if ((rc = reserve(ctx, ctx->tail_recs, cap_n * sizeof(PmTailRec)))) return rc;
+        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.max_rr;
+        a.tail_recs = (PmTailRec *)ctx->tail_recs.p + tail_off;
+        const void *kfn = (const void *)pm_ws_kernel;
+        if (int arc = allow_max_smem(ctx, kfn)) return arc;
+        long long grid = ctx->sm_count;
+        if (grid > n) grid = n;
+        if (grid < 1) grid = 1;
+        if (getenv("SID_DEBUG"))
+            fprintf(stderr, "[sid] launch: ws smem=%d nab=%d ks=%d npairs=%d nslots=%d slot_bytes=%d npanels=%d wrows=%d n16max=%d grid=%lld\n",
+                    wg.smem_bytes, wg.nab, wg.ks, wg.npairs, wg.nslots, wg.slot_bytes, wg.npanels, wg.wrows, wg.n16max, grid);
+        void *params_ws[] = {(void *)&a, (void *)&wg, (void *)&tmap};
+        if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
+        CU(cudaEventRecord(ctx->k_ev[0], st));
+        CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)WS_THREADS), params_ws, (size_t)wg.smem_bytes, st));
+        CU(cudaEventRecord(ctx->k_ev[1], st));
+        ctx->k_ev_valid = true;
+        ctx->launches += 1;
+        const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
+        if (int arc = allow_max_smem(ctx, (const void *)pm_tail_kernel)) return arc;
+        pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, st>>>(a);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        return SID_OK;
+    }
     if (want_tc && pm_tc_geometry(s, Rmax, Wmax, n_angles, tg) && make_window_tensor_map(ctx, &tmap, 16, tg.load_rows)) use_tc = true;
     // Measured (profiles/r02_ab_tc_vs_imma.txt): with one CTA per SM (tensor memory > 256 columns: search radius ~100) the
     // latency-bound non-MAC phases make the tcgen05 kernel slower than the mma.sync kernel at three CTAs per SM, so the

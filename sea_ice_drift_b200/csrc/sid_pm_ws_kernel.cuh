@@ -1,0 +1,670 @@
+// sid_pm_ws_kernel.cuh -- warp-specialised pattern-matching kernel (round 2, second tcgen05 formulation).
+//
+// Same per-point work and arithmetic contract as pm_tc_kernel / pm_points_kernel (reference pmlib.py:176-212 and
+// everything it calls), organised as a pipeline of specialised warps over a stream of grid points, one persistent
+// CTA per SM:
+//
+//   control (1 warp)   work stealing, window rectangle (pmlib.py:200-202), TMA of the window into a ring of 3 slots
+//   gather  (4 warps)  get_template (pmlib.py:89-115): 4 pixels per thread -> compact rows; template sums / zero flag;
+//                      then the Toeplitz EXPANSION of every pair of template rows into a ring of A-operand slots
+//   mma     (4 warps)  one issuing thread each (one x block of 16 result columns each): tcgen05.mma kind::i8,
+//                      A and B both from shared memory, accumulators in tensor memory (2 sets of 256 columns)
+//   stats   (4 warps)  window sums / sums of squares (sliding, exact integers), FP64 denominators
+//   epilogue(2 x 4 warps, alternate points)  tcgen05.ld, combine the two row parities, approximate float screening
+//                      of the angles, OpenCV's exact FP64 normalisation of the winning angle only, argmax, hand-off of
+//                      the winning map to pm_tail_kernel
+//
+// Formulation.  With x' = x + (x0 & 15) = 16 xq + dx (the window is staged from a 16-byte aligned column):
+//
+//   corr[a][y][x] = sum_i sum_j W[y+i][x'+j] T_a[i][j]
+//   D_xq[(dx, a, ip)][n] += sum_k A_pr[(dx, a, ip)][k] * B_{pr,xq}[n][k]        pr = 0 .. ceil(s/2)-1  (row pairs)
+//       A_pr[(dx, a, ip)][k] = T_a[2 pr + ip][k - dx]     (0 outside the row)   -- 16 byte shifts x 3 angles x 2 rows = 96
+//       B_{pr,xq}[n][k]      = W[2 pr + n][16 xq + k]                           -- the staged window itself (16-byte
+//                                                                                  column panels: no im2col, no copy)
+//   corr[a][y][x] = D_xq[(dx,a,0)][y] + D_xq[(dx,a,1)][y+1]
+//
+// so the only operand that has to be GENERATED is 16 byte-shifted copies of each template row (per 4 template pixels:
+// 2 loads, 3 byte permutes, 16 word stores), instead of one Toeplitz row per result column.  Per point and angle
+// batch this is ~1.5 k warp instructions against ~16 k for the row loop of pm_tc_kernel.
+//
+// The exact FP64 normalisation (the most expensive per-output step) runs for the winning angle only: every angle is
+// first screened with a float approximation whose error (< 5e-7) is far below the margin (4e-6) used to decide which
+// angles can still win; angles inside the margin are all evaluated exactly, so the result is the same bit pattern the
+// other kernels produce (strict '>' over angles, np.argmax inside a map).
+#pragma once
+#include "sid_pm_tc_kernel.cuh"
+
+namespace sid {
+
+constexpr int WS_THREADS = 672;           // 21 warps: control | 4 mma | 4 gather | 4 stats | 2 x 4 epilogue
+constexpr int WS_W_MMA = 1, WS_W_GATHER = 5, WS_W_STATS = 9, WS_W_EPI = 13;
+constexpr int WS_NWIN = 3;                // window ring
+constexpr int WS_NENT = 8;                // point entries / template records
+constexpr int WS_MAX_SLOTS = 8;
+constexpr int WS_ACC_COLS = 256;          // tensor-memory columns per accumulator set (4 x blocks x 64)
+constexpr float WS_MARGIN = 4e-6f;
+
+struct PmWsCfg {
+    int nab;          // angles per batch (<= 3)
+    int ks;           // 32-byte K steps per A row
+    int npairs;       // template row pairs = ceil(s / 2)
+    int nwords;       // 32-bit words per compact template row = ceil(s / 4)
+    int tw;           // compact row pitch (words) = nwords + 2 (a zero word either side)
+    int nslots;       // A ring depth
+    int lbo_a;        // bytes between K panels of an A slot
+    int slot_bytes;
+    int wrows;        // rows per window panel
+    int npanels;      // panels per window slot
+    int np_load;      // panels loaded per point
+    int load_rows;    // TMA box height
+    int win_bytes;    // one window slot
+    int n16max;       // widest accumulator (<= 64)
+    int hp;           // pitch of the transposed horizontal sums (odd)
+    int cpl;          // words per angle plane of the combined correlation buffer
+    int hs_words;     // words per transposed horizontal-sum array
+    unsigned inv_nw1; // ceil(2^32 / (nwords + 1))
+    int off_a, off_tpl, tpl_buf_words, off_stat, stat_bytes, off_hs, off_c, smem_bytes;
+};
+
+inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, PmWsCfg &g) {
+    if (s < 2 || s > 112 || Rmax < 2) return false;
+    if (Rmax + 1 > 64 || Rmax + 15 > 64 || Wmax > 256) return false;
+    g.nab = n_angles < 3 ? n_angles : 3;
+    g.npairs = (s + 1) / 2;
+    g.nwords = (s + 3) / 4;
+    g.tw = g.nwords + 2;
+    g.ks = (g.nwords + 4 + 7) / 8;
+    g.lbo_a = 2048 + 16;
+    g.slot_bytes = 2 * g.ks * g.lbo_a;
+    g.nslots = 6;
+    g.n16max = (Rmax + 1 + 15) & ~15;
+    g.np_load = (Wmax + 15 + 15) / 16;
+    g.npanels = 4 + 2 * g.ks;
+    if (g.npanels < g.np_load) g.npanels = g.np_load;
+    g.load_rows = Wmax;
+    g.wrows = (Wmax + 7) & ~7;
+    g.win_bytes = g.npanels * g.wrows * 16;
+    g.hp = Wmax | 1;
+    g.cpl = (max_rr + 31) & ~31;
+    g.inv_nw1 = (unsigned)((0x100000000ull + (unsigned)g.nwords) / (unsigned)(g.nwords + 1));
+    g.tpl_buf_words = g.nab * s * g.tw;
+    size_t off = (size_t)WS_NWIN * g.win_bytes;
+    // the MMAs may read up to s + 64 rows of a panel: keep that inside the allocation behind the last window slot
+    off = (off + 127) & ~(size_t)127;
+    g.off_a = (int)off; off += (size_t)g.nslots * g.slot_bytes;
+    off = (off + 127) & ~(size_t)127;
+    g.off_tpl = (int)off; off += (size_t)2 * g.tpl_buf_words * 4;
+    off = (off + 127) & ~(size_t)127;
+    g.off_stat = (int)off;
+    g.stat_bytes = (max_rr * 12 + 127) & ~127;
+    off += (size_t)2 * g.stat_bytes;
+    g.hs_words = Rmax * g.hp;
+    g.off_hs = (int)off; off += (size_t)2 * g.hs_words * 4;
+    off = (off + 127) & ~(size_t)127;
+    g.off_c = (int)off; off += (size_t)2 * g.nab * g.cpl * 4;
+    g.smem_bytes = (int)((off + 127) & ~(size_t)127);
+    return true;
+}
+
+struct WsPoint { double c1, r1; long long pt, pi; int x0, y0, W, H; int done, pad; };
+struct WsTplRec { long long pt, pi; int x0, W, H, zero; uint32_t tsum[3], tsq[3]; };
+struct WsBars {
+    unsigned long long win_full[WS_NWIN], win_empty[WS_NWIN];
+    unsigned long long slot_full[WS_MAX_SLOTS], slot_empty[WS_MAX_SLOTS];
+    unsigned long long acc_full[2], acc_empty[2];
+    unsigned long long tpl_full[WS_NENT];
+    unsigned long long stats_full[2], stats_empty[2];
+};
+struct WsEpi { TemplStats st[3]; float m[4][3]; unsigned long long key[4]; };
+
+// try_wait spin with a watchdog: a protocol error becomes a trap (launch failure), never a hung GPU
+__device__ __forceinline__ void ws_wait(uint32_t bar, unsigned parity) {
+    unsigned spins = 0;
+    long long t0 = 0;
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        ++spins;
+        if (spins == 64u) t0 = clock64();
+        if (spins > 64u && (spins & 255u) == 0u && clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void ws_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ws_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor], u8 x u8 -> s32, M = 128
+__device__ __forceinline__ void tc_mma_i8_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+
+// exact normalisation of one angle (OpenCV's formula, bit for bit the other kernels' epilogue); optional map store
+__device__ __forceinline__ unsigned long long ws_exact_pass(const int32_t *__restrict__ Ca, const uint32_t *__restrict__ wsum,
+                                                            const double *__restrict__ wden, const TemplStats st, int RR, int et,
+                                                            float *__restrict__ dst) {
+    float bv = -INFINITY;
+    int bidx = -1;
+    for (int base = 0; base < RR; base += 512) {
+        double num[4], tt[4];
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int idx = min(base + 128 * c + et, RR - 1);
+            num[c] = __dsub_rn((double)Ca[idx], __dmul_rn((double)wsum[idx], st.mean));
+            tt[c] = __dmul_rn(wden[idx], st.norm);
+        }
+        ncc_finish4(num, tt, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int idx = base + 128 * c + et;
+            if (idx < RR) {
+                const float vv = st.flat ? 1.0f : v[c];
+                if (dst) dst[idx] = vv;
+                if (vv > bv) { bv = vv; bidx = idx; }
+            }
+        }
+    }
+    return bidx >= 0 ? peak_key(bv, (uint32_t)bidx) : 0ull;
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMap tmapP) {
+    extern __shared__ __align__(128) unsigned char ws_smem[];
+    __shared__ WsBars B;
+    __shared__ WsPoint ent[WS_NENT];
+    __shared__ WsTplRec trec[WS_NENT];
+    __shared__ WsEpi epi[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int all_done_s;
+    __shared__ volatile unsigned total_pts_s[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = a.s, nab = g.nab;
+    const int PS = g.wrows * 16;
+    const int A_ = a.n_angles;
+    const int nbatch = (A_ + nab - 1) / nab;
+    const int per = (A_ + nbatch - 1) / nbatch;
+    uint8_t *sWin = ws_smem;
+    uint8_t *sA = ws_smem + g.off_a;
+    uint32_t *sTpl = reinterpret_cast<uint32_t *>(ws_smem + g.off_tpl);
+    const uint32_t bar0 = smem_u32(&B);
+    auto BAR = [&](const unsigned long long *p) -> uint32_t { return bar0 + (uint32_t)((const unsigned char *)p - (const unsigned char *)&B); };
+
+    // ---- one-time setup: zero the A ring and the template buffers (their padding stays zero for good)
+    for (int t = tid; t < (g.off_stat - g.off_a) / 4; t += WS_THREADS) reinterpret_cast<uint32_t *>(sA)[t] = 0u;
+    if (tid < WS_NENT) { trec[tid].zero = 0; for (int k = 0; k < 3; ++k) { trec[tid].tsum[k] = 0u; trec[tid].tsq[k] = 0u; } }
+    if (tid == 0) {
+        for (int i = 0; i < WS_NWIN; ++i) { mbar_init(&B.win_full[i], 1); mbar_init(&B.win_empty[i], 8); }
+        for (int i = 0; i < WS_MAX_SLOTS; ++i) { mbar_init(&B.slot_full[i], 1); mbar_init(&B.slot_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&B.acc_full[i], 4); mbar_init(&B.acc_empty[i], 4);
+            mbar_init(&B.stats_full[i], 4); mbar_init(&B.stats_empty[i], 4);
+        }
+        for (int i = 0; i < WS_NENT; ++i) mbar_init(&B.tpl_full[i], 4);
+        all_done_s = 0; total_pts_s[0] = 0u; total_pts_s[1] = 0u;
+    }
+    if (warp == 0) tc_alloc(&tmem_base_s, 512u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+
+    if (warp == 0) {
+        // ================================================================ control
+        if (lane == 0) {
+            const unsigned win_tx = (unsigned)(g.np_load * g.load_rows * 16);
+            unsigned P = 0;
+            unsigned pi = atomicAdd(a.counter, 1u);
+            while ((long long)pi < a.n) {
+                const long long pt = a.order ? (long long)a.order[pi] : (long long)pi;
+                const double c1 = a.c1[pt], r1 = a.r1[pt], c2 = a.c2fg[pt], r2 = a.r2fg[pt], brd = a.border[pt];
+                const unsigned pi_next = atomicAdd(a.counter, 1u);
+                long long x0, y0; int W, H;
+                bool ok = pm_window_rect(a, c1, r1, c2, r2, brd, x0, y0, W, H);
+                if (ok) {
+                    const int RH = H - s + 1, RW = W - s + 1, xoff = (int)(x0 & 15);
+                    ok = RH * RW <= a.max_rr && H <= g.load_rows && W + xoff <= g.np_load * 16 && RH + 1 <= g.n16max &&
+                         xoff + RW <= 64;
+                }
+                if (!ok) {
+                    double *o = a.out + 5 * pt;
+                    o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
+                    if (a.status) a.status[pt] = -1;
+                    a.tail_recs[pi].pt = -1;
+                } else {
+                    const unsigned ws = P % WS_NWIN;
+                    if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u);
+                    WsPoint &e = ent[P & (WS_NENT - 1)];
+                    e.c1 = c1; e.r1 = r1; e.pt = pt; e.pi = (long long)pi;
+                    e.x0 = (int)x0; e.y0 = (int)y0; e.W = W; e.H = H; e.done = 0;
+                    mbar_expect_tx(&B.win_full[ws], win_tx);
+                    const int xa = (int)x0 - (int)(x0 & 15);
+                    for (int p = 0; p < g.np_load; ++p)
+                        tma_load_2d(sWin + (size_t)ws * g.win_bytes + (size_t)p * PS, &tmapP, xa + 16 * p, (int)y0, &B.win_full[ws]);
+                    ++P;
+                }
+                pi = pi_next;
+            }
+            const unsigned ws = P % WS_NWIN;
+            if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u);
+            ent[P & (WS_NENT - 1)].done = 1;
+            ws_arrive(BAR(&B.win_full[ws]));
+        }
+    } else if (warp < WS_W_GATHER) {
+        // ================================================================ mma issuers (x block w each)
+        if (lane == 0) {
+            const int w = warp - WS_W_MMA;
+            unsigned P = 0, round = 0, use0 = 0, use1 = 0;
+            int slot = 0;
+            const uint64_t adesc0 = tc_smem_desc(smem_u32(sA), (uint32_t)g.lbo_a, 128u);
+            for (;;) {
+                const unsigned ws = P % WS_NWIN;
+                ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u);
+                const WsPoint &e = ent[P & (WS_NENT - 1)];
+                if (e.done) break;
+                const int RH = e.H - s + 1, RW = e.W - s + 1, xoff = e.x0 & 15;
+                const int nxq = (xoff + RW + 15) >> 4;
+                const int n16 = (RH + 1 + 15) & ~15;
+                const uint32_t idesc = tc_idesc_u8(n16);
+                const unsigned set = P & 1u;
+                const uint32_t dcol = tbase + set * WS_ACC_COLS + (uint32_t)(w * 64);
+                const uint64_t bdesc0 = tc_smem_desc(smem_u32(sWin + (size_t)ws * g.win_bytes + (size_t)w * PS), (uint32_t)PS, 128u);
+                for (int b = 0; b < nbatch; ++b) {
+                    const unsigned use = set ? use1 : use0;
+                    if (use >= 1u) ws_wait(BAR(&B.acc_empty[set]), (use - 1u) & 1u);
+                    tc_fence_after();
+                    for (int pr = 0; pr < g.npairs; ++pr) {
+                        ws_wait(BAR(&B.slot_full[slot]), round);
+                        tc_fence_after();
+                        if (w < nxq) {
+                            const uint64_t ad = adesc0 + (uint64_t)((slot * g.slot_bytes) >> 4);
+                            const uint64_t bd = bdesc0 + (uint64_t)(2 * pr);
+                            for (int kk = 0; kk < g.ks; ++kk)
+                                tc_mma_i8_ss(dcol, ad + (uint64_t)((kk * 2 * g.lbo_a) >> 4), bd + (uint64_t)((kk * 2 * PS) >> 4), idesc,
+                                             (pr | kk) ? 1u : 0u);
+                        }
+                        tc_commit_addr(BAR(&B.slot_empty[slot]));
+                        if (++slot == g.nslots) { slot = 0; round ^= 1u; }
+                    }
+                    tc_commit_addr(BAR(&B.acc_full[set]));
+                    if (set) ++use1; else ++use0;
+                }
+                tc_commit_addr(BAR(&B.win_empty[ws]));
+                ++P;
+            }
+            if (w == 0) {
+                total_pts_s[0] = (P + 1u) / 2u; total_pts_s[1] = P / 2u;
+                __threadfence_block();
+                all_done_s = 1;
+                __threadfence_block();
+            }
+            // poison completion of both accumulator barriers (the epilogue groups leave on it)
+            if (use0 >= 1u) ws_wait(BAR(&B.acc_empty[0]), (use0 - 1u) & 1u);
+            ws_arrive(BAR(&B.acc_full[0]));
+            if (use1 >= 1u) ws_wait(BAR(&B.acc_empty[1]), (use1 - 1u) & 1u);
+            ws_arrive(BAR(&B.acc_full[1]));
+        }
+    } else if (warp < WS_W_STATS) {
+        // ================================================================ gather + Toeplitz expansion
+        const int gt = tid - WS_W_GATHER * 32, gw = warp - WS_W_GATHER;
+        const int nwords = g.nwords, tw = g.tw;
+        const int rows_per_pass = 128 / nwords;
+        const int gi = gt / nwords, wj = gt - gi * nwords;
+        const bool active = gi < rows_per_pass;
+        double djv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) djv[k] = (double)min(4 * wj + k, s - 1);     // columns past the row repeat the last one (discarded)
+        unsigned P = 0, J = 0, q = 0;
+        for (;;) {
+            const unsigned ws = P % WS_NWIN;
+            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u);
+            const WsPoint &e = ent[P & (WS_NENT - 1)];
+            if (e.done) break;
+            const double c1 = e.c1, r1 = e.r1;
+            const long long e_pt = e.pt, e_pi = e.pi;
+            const int e_x0 = e.x0, e_W = e.W, e_H = e.H;
+            for (int a0 = 0; a0 < A_; a0 += per, ++J) {
+                const int nb = min(per, A_ - a0);
+                uint32_t *buf = sTpl + (J & 1u) * g.tpl_buf_words;
+                WsTplRec &tr = trec[J & (WS_NENT - 1)];
+                // which angles can skip the bounds checks (warp-uniform)
+                unsigned inside_mask = 0;
+                for (int ai = 0; ai < nb; ++ai) {
+                    const double *tab = a.tab + 4 * (a0 + ai);
+                    if (template_inside_warp(a.rows1, a.cols1, __dsub_rn(r1, tab[2]), __dsub_rn(c1, tab[3]), tab[0], tab[1], s))
+                        inside_mask |= 1u << ai;
+                }
+                if (active) {
+                    uint32_t lsum = 0, lsq = 0;
+                    int lzero = 0, cur_a = -1;
+                    for (int R = gi; R < nb * s; R += rows_per_pass) {
+                        const int ai = (R >= s) + (R >= 2 * s), i = R - ai * s;
+                        if (ai != cur_a) {
+                            if (cur_a >= 0) { atomicAdd(&tr.tsum[cur_a], lsum); atomicAdd(&tr.tsq[cur_a], lsq); }
+                            lsum = 0; lsq = 0; cur_a = ai;
+                        }
+                        const double *tab = a.tab + 4 * (a0 + ai);
+                        const double cs = tab[0], sn = tab[1];
+                        const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
+                        const double di = (double)i;
+                        const double br = __dadd_rn(off0, __dmul_rn(di, cs));
+                        const double bc = __dadd_rn(off1, __dmul_rn(di, -sn));
+                        const bool inside = (inside_mask >> ai) & 1u;
+                        uint32_t word = 0;
+                        if (inside && a.rot_order == 0) {
+                            uint32_t v[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const double row = __dadd_rn(br, __dmul_rn(djv[k], sn));
+                                const double col = __dadd_rn(bc, __dmul_rn(djv[k], cs));
+                                v[k] = template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (4 * wj + k < s) { word |= v[k] << (8 * k); lsum += v[k]; lsq += v[k] * v[k]; lzero |= (v[k] == 0u); }
+                        } else {
+#pragma unroll 1
+                            for (int k = 0; k < 4; ++k) {
+                                if (4 * wj + k < s) {
+                                    const double row = __dadd_rn(br, __dmul_rn(djv[k], sn));
+                                    const double col = __dadd_rn(bc, __dmul_rn(djv[k], cs));
+                                    const uint32_t v = inside ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order)
+                                                              : template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order);
+                                    word |= v << (8 * k); lsum += v; lsq += v * v; lzero |= (v == 0u);
+                                }
+                            }
+                        }
+                        buf[(ai * s + i) * tw + 1 + wj] = word;
+                    }
+                    if (cur_a >= 0) { atomicAdd(&tr.tsum[cur_a], lsum); atomicAdd(&tr.tsq[cur_a], lsq); }
+                    if (lzero) tr.zero = 1;
+                }
+                if (gt == 0) { tr.pt = e_pt; tr.pi = e_pi; tr.x0 = e_x0; tr.W = e_W; tr.H = e_H; }
+                if (gt == 32) {          // clear the record of the next job (nobody reads it any more)
+                    WsTplRec &nx = trec[(J + 1u) & (WS_NENT - 1)];
+                    nx.zero = 0;
+                    for (int k = 0; k < 3; ++k) { nx.tsum[k] = 0u; nx.tsq[k] = 0u; }
+                }
+                ws_bar(1, 128);
+                if (lane == 0) ws_arrive(BAR(&B.tpl_full[J & (WS_NENT - 1)]));
+                // ---- expansion: row pair pr -> A slot (q + pr) % nslots
+                const int ntask = 2 * nb * (nwords + 1);
+                for (int pr = gw; pr < g.npairs; pr += 4) {
+                    const unsigned qq = q + (unsigned)pr;
+                    const unsigned use = qq / (unsigned)g.nslots, slot = qq - use * (unsigned)g.nslots;
+                    if (use >= 1u) ws_wait(BAR(&B.slot_empty[slot]), (use - 1u) & 1u);
+                    uint8_t *sl = sA + (size_t)slot * g.slot_bytes;
+                    for (int t = lane; t < ntask; t += 32) {
+                        const int rest = (int)__umulhi((unsigned)t, g.inv_nw1);
+                        const int wjj = t - rest * (nwords + 1);
+                        const int ai = rest >> 1, ip = rest & 1;
+                        const int i = 2 * pr + ip;
+                        uint32_t wlo = 0, whi = 0;
+                        if (i < s) {
+                            const uint32_t *rowp = buf + (ai * s + i) * tw + wjj;
+                            wlo = rowp[0]; whi = rowp[1];
+                        }
+                        uint32_t f[4];
+                        f[0] = whi;
+                        f[1] = __byte_perm(wlo, whi, 0x6543);
+                        f[2] = __byte_perm(wlo, whi, 0x5432);
+                        f[3] = __byte_perm(wlo, whi, 0x4321);
+                        uint8_t *rowbase = sl + (2 * ai + ip) * 16;
+#pragma unroll
+                        for (int ee = 0; ee < 4; ++ee) {
+                            const int wq = wjj + ee;
+                            uint8_t *pw = rowbase + (wq >> 2) * g.lbo_a + (wq & 3) * 4 + ee * 4 * 128;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint32_t *>(pw + c * 128) = f[c];
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) ws_arrive(BAR(&B.slot_full[slot]));
+                }
+                q += (unsigned)g.npairs;
+            }
+            ++P;
+        }
+    } else if (warp < WS_W_EPI) {
+        // ================================================================ window statistics
+        const int st_ = tid - WS_W_STATS * 32;
+        uint32_t *hsT = reinterpret_cast<uint32_t *>(ws_smem + g.off_hs);
+        uint32_t *hqT = hsT + g.hs_words;
+        const int hp = g.hp;
+        unsigned P = 0;
+        for (;;) {
+            const unsigned ws = P % WS_NWIN;
+            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u);
+            const WsPoint &e = ent[P & (WS_NENT - 1)];
+            if (e.done) break;
+            const int W = e.W, H = e.H, xoff = e.x0 & 15;
+            const int RH = H - s + 1, RW = W - s + 1;
+            const unsigned set = P & 1u;
+            if (P >= 2u) ws_wait(BAR(&B.stats_empty[set]), ((P >> 1) - 1u) & 1u);
+            double *wden = reinterpret_cast<double *>(ws_smem + g.off_stat + (size_t)set * g.stat_bytes);
+            uint32_t *wsum = reinterpret_cast<uint32_t *>(wden + a.max_rr);
+            const uint8_t *win = sWin + (size_t)ws * g.win_bytes;
+            // horizontal sliding sums, one window row per thread
+            for (int r = st_; r < H; r += 128) {
+                const uint8_t *rowp = win + 16 * r;
+                auto wb = [&](int k) -> uint32_t { const int kk = k + xoff; return rowp[(kk >> 4) * PS + (kk & 15)]; };
+                uint32_t sum = 0, sq = 0;
+                for (int j = 0; j < s; ++j) { const uint32_t v = wb(j); sum += v; sq += v * v; }
+                for (int x = 0; x < RW; ++x) {
+                    hsT[x * hp + r] = sum; hqT[x * hp + r] = sq;
+                    const uint32_t va = wb(x), vb = wb(x + s);       // x + s <= W: the staged panels hold that column
+                    sum += vb - va; sq += vb * vb - va * va;
+                }
+            }
+            ws_bar(2, 128);
+            if (lane == 0) ws_arrive(BAR(&B.win_empty[ws]));        // this warp is done with the window
+            // vertical sliding sums -> window sum and denominator per displacement
+            {
+                int nseg = 128 / RW;
+                if (nseg < 1) nseg = 1;
+                if (nseg > RH) nseg = RH;
+                const int L = (RH + nseg - 1) / nseg;
+                for (int t = st_; t < RW * nseg; t += 128) {
+                    const int sg = t / RW, x = t - sg * RW;
+                    const int ys = sg * L, ye = min(RH, ys + L);
+                    if (ys >= ye) continue;
+                    const uint32_t *hs = hsT + x * hp, *hq = hqT + x * hp;
+                    uint32_t sum = 0, sq = 0;
+                    for (int i = 0; i < s; ++i) { sum += hs[ys + i]; sq += hq[ys + i]; }
+                    for (int y = ys; y < ye; ++y) {
+                        wsum[y * RW + x] = sum;
+                        wden[y * RW + x] = window_den(sum, sq, a.inv_area);
+                        if (y + 1 < ye) { sum += hs[y + s] - hs[y]; sq += hq[y + s] - hq[y]; }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ws_arrive(BAR(&B.stats_full[set]));
+            ws_bar(2, 128);                                          // hsT / hqT are free again
+            ++P;
+        }
+    } else {
+        // ================================================================ epilogue groups (points P = e, e + 2, ...)
+        const int eg = (warp - WS_W_EPI) >> 2;
+        const int et = tid - (WS_W_EPI + 4 * eg) * 32;
+        const int ew = et >> 5;
+        const int quarter = warp & 3;
+        const int barid = 3 + eg;
+        WsEpi &E = epi[eg];
+        int32_t *C = reinterpret_cast<int32_t *>(ws_smem + g.off_c) + (size_t)eg * nab * g.cpl;
+        const double *wden = reinterpret_cast<const double *>(ws_smem + g.off_stat + (size_t)eg * g.stat_bytes);
+        const uint32_t *wsum = reinterpret_cast<const uint32_t *>(wden + a.max_rr);
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const int dx = 4 * quarter + (lane >> 3), aa = (lane >> 1) & 3, ip = lane & 1;
+        const long long Nll = (long long)s * (long long)s;
+        unsigned acc_use = 0, stat_use = 0;
+        bool leave = false;
+        for (unsigned n = 0; !leave; ++n) {
+            const unsigned P = (unsigned)eg + 2u * n;
+            float best_r = -INFINITY;
+            int best_a = -1, best_idx = 0;
+            bool invalid = false;
+            long long pt = 0, pi = 0;
+            int W = 0, H = 0, xoff = 0, RH = 0, RW = 0, RR = 0;
+            for (int b = 0; b < nbatch; ++b) {
+                const unsigned J = P * (unsigned)nbatch + (unsigned)b;
+                ws_wait(BAR(&B.acc_full[eg]), acc_use & 1u); ++acc_use;
+                if (b == 0 && all_done_s && n == total_pts_s[eg]) { leave = true; break; }
+                tc_fence_after();
+                ws_wait(BAR(&B.tpl_full[J & (WS_NENT - 1)]), (J >> 3) & 1u);
+                const WsTplRec &tr = trec[J & (WS_NENT - 1)];
+                if (b == 0) {
+                    pt = tr.pt; pi = tr.pi; W = tr.W; H = tr.H; xoff = tr.x0 & 15;
+                    RH = H - s + 1; RW = W - s + 1; RR = RH * RW;
+                    ws_wait(BAR(&B.stats_full[eg]), stat_use & 1u); ++stat_use;
+                }
+                const int a0 = b * per, nb = min(per, A_ - a0);
+                const bool zero = tr.zero != 0;
+                uint32_t tsum[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tsum[k] = tr.tsum[k];
+                if (et < nb) E.st[et] = templ_stats(tr.tsum[et], tr.tsq[et], a.inv_area, a.sqrt_inv_area);
+                if (!invalid && !zero) {
+                    // ---- combined correlation numerators -> C[a][y * RW + x]
+                    const int nxq = (xoff + RW + 15) >> 4;
+                    const int n16 = (RH + 1 + 15) & ~15;
+                    for (int xq = 0; xq < nxq; ++xq) {
+                        const int xw = 16 * xq + 4 * quarter - xoff;            // first x of this warp's four dx
+                        if (xw + 3 < 0 || xw >= RW) continue;                   // warp-uniform
+                        const int x = 16 * xq + dx - xoff;
+                        const bool lane_ok = x >= 0 && x < RW && aa < nb;
+                        int32_t *cp = C + aa * g.cpl + x;
+                        uint32_t carry = 0;
+                        for (int c0 = 0; c0 < n16; c0 += 16) {
+                            uint32_t r[16];
+                            tc_ld16(tbase + (uint32_t)eg * WS_ACC_COLS + (uint32_t)(xq * 64 + c0) + lane_base, r);
+                            tc_ld_wait();
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const uint32_t send = ip ? r[2 * t + 1] : (t ? r[t ? 2 * t - 1 : 0] : carry);
+                                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                                const int y = c0 + 2 * t - ip;
+                                const uint32_t val = r[2 * t] + recv;
+                                if (lane_ok && y >= 0 && y < RH) cp[y * RW] = (int32_t)val;
+                            }
+                            carry = r[15];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ws_arrive(BAR(&B.acc_empty[eg]));
+                if (zero) invalid = true;
+                ws_bar(barid, 128);
+                if (invalid) continue;
+
+                // ---- float screening: an upper estimate (error < 5e-7) of every angle's maximum
+                float m[3] = {-INFINITY, -INFINITY, -INFINITY};
+                float sc[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sc[k] = (k < nb && !E.st[k].flat) ? (float)(1.0 / ((double)Nll * E.st[k].norm)) : 0.0f;
+                for (int idx = et; idx < RR; idx += 128) {
+                    const long long wsv = (long long)wsum[idx];
+                    const float wd = (float)wden[idx];
+                    float inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(wd));
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (k < nb) {
+                            const long long n64 = (long long)C[k * g.cpl + idx] * Nll - wsv * (long long)tsum[k];
+                            const float qv = __ll2float_rn(n64) * sc[k] * inv;
+                            float v = fabsf(qv) < 0.99999f ? qv : 1.0f;
+                            if (wd == 0.0f) v = 0.0f;
+                            m[k] = fmaxf(m[k], v);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float v = m[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    if (lane == 0) E.m[ew][k] = v;
+                }
+                ws_bar(barid, 128);
+                float M[3], Mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    M[k] = fmaxf(fmaxf(E.m[0][k], E.m[1][k]), fmaxf(E.m[2][k], E.m[3][k]));
+                    if (k < nb && E.st[k].flat) M[k] = 1.0f;
+                    if (k >= nb) M[k] = -INFINITY;
+                    Mx = fmaxf(Mx, M[k]);
+                }
+                const float thr = fmaxf(Mx, best_r) - WS_MARGIN;
+                int ncont = 0, first = -1;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) if (k < nb && M[k] >= thr) { ++ncont; if (first < 0) first = k; }
+                float *dst = a.tail_maps + (size_t)pi * a.max_rr;
+                // group-wide maximum of a key (all threads return the same value)
+                auto group_max = [&](unsigned long long key) -> unsigned long long {
+                    key = warp_max_u64(key);
+                    ws_bar(barid, 128);                      // E.key free (previous readers done)
+                    if (lane == 0) E.key[ew] = key;
+                    ws_bar(barid, 128);
+                    unsigned long long k0 = E.key[0], k1 = E.key[1], k2 = E.key[2], k3 = E.key[3];
+                    k0 = k0 > k1 ? k0 : k1; k2 = k2 > k3 ? k2 : k3;
+                    return k0 > k2 ? k0 : k2;
+                };
+                if (ncont == 1 && M[first] > best_r + WS_MARGIN) {
+                    const unsigned long long key = group_max(ws_exact_pass(C + first * g.cpl, wsum, wden, E.st[first], RR, et, dst));
+                    best_r = key_f32((uint32_t)(key >> 32));
+                    best_idx = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+                    best_a = a0 + first;
+                } else {
+                    int pending = -1;
+                    for (int k = 0; k < nb; ++k) {
+                        if (!(M[k] >= thr)) continue;
+                        const unsigned long long key = group_max(ws_exact_pass(C + k * g.cpl, wsum, wden, E.st[k], RR, et, nullptr));
+                        const float v = key_f32((uint32_t)(key >> 32));
+                        if (v > best_r) {
+                            best_r = v; best_idx = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+                            best_a = a0 + k; pending = k;
+                        }
+                    }
+                    if (pending >= 0) (void)ws_exact_pass(C + pending * g.cpl, wsum, wden, E.st[pending], RR, et, dst);
+                }
+                ws_bar(barid, 128);          // C and E.st are free for the next batch
+            }
+            if (leave) break;
+            __syncwarp();
+            if (lane == 0) ws_arrive(BAR(&B.stats_empty[eg]));
+            if (et == 0) {
+                if (invalid || best_a < 0) {
+                    double *o = a.out + 5 * pt;
+                    o[0] = o[1] = o[2] = o[3] = o[4] = nan("");
+                    if (a.status) a.status[pt] = 0;
+                    a.tail_recs[pi].pt = -1;
+                } else {
+                    PmTailRec rec;
+                    rec.pt = (int)pt; rec.RH = RH; rec.RW = RW; rec.H = H; rec.W = W;
+                    rec.best_idx = best_idx; rec.best_a = best_a; rec.best_r = best_r;
+                    a.tail_recs[pi] = rec;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tc_dealloc(tbase, 512u); }
+}
+
+}  // namespace sid
