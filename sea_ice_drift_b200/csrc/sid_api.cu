@@ -228,7 +228,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     memset(&wg, 0, sizeof wg);
     bool use_ws = false;
     if (want_ws && split_tail && pm_ws_geometry(s, Rmax, Wmax, n_angles, a.max_rr, wg) &&
-        (size_t)wg.smem_bytes + 8192 <= (size_t)ctx->max_smem_optin && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows))
+        (size_t)wg.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows))
         use_ws = true;
     if (use_ws) {
         a.tma = 1; a.ab = wg.nab;
@@ -250,6 +250,11 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         if (getenv("SID_DEBUG"))
             fprintf(stderr, "[sid] launch: ws smem=%d nab=%d ks=%d npairs=%d nslots=%d slot_bytes=%d npanels=%d wrows=%d n16max=%d grid=%lld\n",
                     wg.smem_bytes, wg.nab, wg.ks, wg.npairs, wg.nslots, wg.slot_bytes, wg.npanels, wg.wrows, wg.n16max, grid);
+#ifdef SID_WS_PROF
+        if ((rc = reserve(ctx, ctx->scratch, (size_t)grid * 6 * 8 * 8))) return rc;
+        CU(cudaMemsetAsync(ctx->scratch.p, 0, (size_t)grid * 6 * 8 * 8, st));
+        a.scratch = (unsigned char *)ctx->scratch.p;
+#endif
         void *params_ws[] = {(void *)&a, (void *)&wg, (void *)&tmap};
         if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
         CU(cudaEventRecord(ctx->k_ev[0], st));
@@ -257,6 +262,23 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         CU(cudaEventRecord(ctx->k_ev[1], st));
         ctx->k_ev_valid = true;
         ctx->launches += 1;
+#ifdef SID_WS_PROF
+        {
+            std::vector<long long> h((size_t)grid * 48);
+            CU(cudaStreamSynchronize(st));
+            CU(cudaMemcpy(h.data(), ctx->scratch.p, h.size() * 8, cudaMemcpyDeviceToHost));
+            static const char *names[6] = {"control", "mma0", "gather0", "stats0", "epi0", "epi1"};
+            const double per_pt = (double)n / (double)grid;
+            for (int r = 0; r < 6; ++r) {
+                fprintf(stderr, "[ws prof] %-8s clk/point:", names[r]);
+                for (int k = 0; k < 8; ++k) {
+                    double sum = 0; for (long long c = 0; c < grid; ++c) sum += (double)h[((size_t)c * 6 + r) * 8 + k];
+                    fprintf(stderr, " %8.0f", sum / (double)grid / per_pt);
+                }
+                fprintf(stderr, "\n");
+            }
+        }
+#endif
         const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
         if (int arc = allow_max_smem(ctx, (const void *)pm_tail_kernel)) return arc;
         pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, st>>>(a);

@@ -36,13 +36,27 @@
 
 namespace sid {
 
-constexpr int WS_THREADS = 672;           // 21 warps: control | 4 mma | 4 gather | 4 stats | 2 x 4 epilogue
-constexpr int WS_W_MMA = 1, WS_W_GATHER = 5, WS_W_STATS = 9, WS_W_EPI = 13;
+constexpr int WS_THREADS = 896;           // 28 warps: control | 4 mma | 8 gather | 7 stats | 2 x 4 epilogue
+constexpr int WS_W_MMA = 1, WS_W_GATHER = 5, WS_W_STATS = 13, WS_W_EPI = 20;
+constexpr int WS_NST = 7 * 32;            // stats threads
+constexpr int WS_NG = 8;                  // gather warps
 constexpr int WS_NWIN = 3;                // window ring
 constexpr int WS_NENT = 8;                // point entries / template records
 constexpr int WS_MAX_SLOTS = 8;
 constexpr int WS_ACC_COLS = 256;          // tensor-memory columns per accumulator set (4 x blocks x 64)
 constexpr float WS_MARGIN = 4e-6f;
+
+// optional role profile (-DSID_WS_PROF): cycles per bucket, written to a.scratch as long long [cta][6 roles][8]
+#ifdef SID_WS_PROF
+#define WSP_DECL long long wsp[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long wsp_t = clock64();
+#define WSP(k) { const long long now_ = clock64(); wsp[k] += now_ - wsp_t; wsp_t = now_; }
+#define WSP_OUT(role) { long long *d_ = reinterpret_cast<long long *>(a.scratch) + ((size_t)blockIdx.x * 6 + (role)) * 8; \
+                        for (int k_ = 0; k_ < 8; ++k_) d_[k_] = wsp[k_]; }
+#else
+#define WSP_DECL
+#define WSP(k) {}
+#define WSP_OUT(role) {}
+#endif
 
 struct PmWsCfg {
     int nab;          // angles per batch (<= 3)
@@ -76,10 +90,11 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     g.ks = (g.nwords + 4 + 7) / 8;
     g.lbo_a = 2048 + 16;
     g.slot_bytes = 2 * g.ks * g.lbo_a;
-    g.nslots = 6;
+    g.nslots = WS_NG;          // >= the number of expanding warps: a warp's successive row pairs then reuse ONE slot, so it can never wait
+                               // for a completion two phases ahead (a parity wait cannot tell phase k from phase k + 2)
     g.n16max = (Rmax + 1 + 15) & ~15;
     g.np_load = (Wmax + 15 + 15) / 16;
-    g.npanels = 4 + 2 * g.ks;
+    g.npanels = 3 + 2 * g.ks;  // x block 3 reads panels 3 .. 2 + 2 ks
     if (g.npanels < g.np_load) g.npanels = g.np_load;
     g.load_rows = Wmax;
     g.wrows = (Wmax + 7) & ~7;
@@ -96,7 +111,7 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     g.off_tpl = (int)off; off += (size_t)2 * g.tpl_buf_words * 4;
     off = (off + 127) & ~(size_t)127;
     g.off_stat = (int)off;
-    g.stat_bytes = (max_rr * 12 + 127) & ~127;
+    g.stat_bytes = (max_rr * 16 + 127) & ~127;           // wden f64 | wsum u32 | 1/wden f32 (before that: the u32 sums of squares)
     off += (size_t)2 * g.stat_bytes;
     g.hs_words = Rmax * g.hp;
     g.off_hs = (int)off; off += (size_t)2 * g.hs_words * 4;
@@ -118,17 +133,40 @@ struct WsBars {
 struct WsEpi { TemplStats st[3]; float m[4][3]; unsigned long long key[4]; };
 
 // try_wait spin with a watchdog: a protocol error becomes a trap (launch failure), never a hung GPU
-__device__ __forceinline__ void ws_wait(uint32_t bar, unsigned parity) {
-    unsigned spins = 0;
-    long long t0 = 0;
+#ifdef SID_WS_DEBUG
+__device__ int g_ws_abort[1024], g_ws_msgs = 0;
+__device__ unsigned g_ws_bar0 = 0;
+__device__ int g_ws_prog[32];
+#define WSD(code) { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) *(volatile int *)&g_ws_prog[threadIdx.x >> 5] = (code); }
+#else
+#define WSD(code) {}
+#endif
+__device__ __forceinline__ void ws_wait(uint32_t bar, unsigned parity, int line = 0) {
+    // try_wait SUSPENDS the thread until the phase completes or the time limit passes; with the default (short) limit the
+    // waiting warps of this kernel spent 55 % of the SM's issue slots re-polling (ncu), so ask for a long one
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000000u) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
     for (;;) {
-        unsigned ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000000u) : "memory");
         if (ok) return;
-        ++spins;
-        if (spins == 64u) t0 = clock64();
-        if (spins > 64u && (spins & 255u) == 0u && clock64() - t0 > 8000000000LL) __trap();
+#ifdef SID_WS_DEBUG
+        if (*(volatile int *)&g_ws_abort[blockIdx.x] || clock64() - t0 > 100000000LL) {
+            if ((threadIdx.x & 31) == 0 && blockIdx.x == 0 && atomicAdd(&g_ws_msgs, 1) < 200)
+                printf("[ws] block %d warp %d lane %d: wait timed out, barrier byte %d parity %u line %d | gather prog %d %d %d %d %d %d %d %d\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+                       (int)(threadIdx.x & 31), (int)(bar - g_ws_bar0), parity, line, g_ws_prog[5], g_ws_prog[6], g_ws_prog[7], g_ws_prog[8],
+                       g_ws_prog[9], g_ws_prog[10], g_ws_prog[11], g_ws_prog[12]);
+            __nanosleep(1000000);
+            g_ws_abort[blockIdx.x] = 1;
+            return;
+        }
+#else
+        // watchdog: a protocol error becomes a trap (launch failure), never a hung GPU
+        if (clock64() - t0 > 8000000000LL) __trap();
+#endif
     }
 }
 __device__ __forceinline__ void ws_arrive(uint32_t bar) {
@@ -200,19 +238,22 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
     uint8_t *sA = ws_smem + g.off_a;
     uint32_t *sTpl = reinterpret_cast<uint32_t *>(ws_smem + g.off_tpl);
     const uint32_t bar0 = smem_u32(&B);
+#ifdef SID_WS_DEBUG
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_ws_bar0 = bar0;
+#endif
     auto BAR = [&](const unsigned long long *p) -> uint32_t { return bar0 + (uint32_t)((const unsigned char *)p - (const unsigned char *)&B); };
 
     // ---- one-time setup: zero the A ring and the template buffers (their padding stays zero for good)
     for (int t = tid; t < (g.off_stat - g.off_a) / 4; t += WS_THREADS) reinterpret_cast<uint32_t *>(sA)[t] = 0u;
     if (tid < WS_NENT) { trec[tid].zero = 0; for (int k = 0; k < 3; ++k) { trec[tid].tsum[k] = 0u; trec[tid].tsq[k] = 0u; } }
     if (tid == 0) {
-        for (int i = 0; i < WS_NWIN; ++i) { mbar_init(&B.win_full[i], 1); mbar_init(&B.win_empty[i], 8); }
+        for (int i = 0; i < WS_NWIN; ++i) { mbar_init(&B.win_full[i], 1); mbar_init(&B.win_empty[i], 4 + WS_NST / 32); }
         for (int i = 0; i < WS_MAX_SLOTS; ++i) { mbar_init(&B.slot_full[i], 1); mbar_init(&B.slot_empty[i], 4); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&B.acc_full[i], 4); mbar_init(&B.acc_empty[i], 4);
-            mbar_init(&B.stats_full[i], 4); mbar_init(&B.stats_empty[i], 4);
+            mbar_init(&B.stats_full[i], WS_NST / 32); mbar_init(&B.stats_empty[i], 4);
         }
-        for (int i = 0; i < WS_NENT; ++i) mbar_init(&B.tpl_full[i], 4);
+        for (int i = 0; i < WS_NENT; ++i) mbar_init(&B.tpl_full[i], WS_NG);
         all_done_s = 0; total_pts_s[0] = 0u; total_pts_s[1] = 0u;
     }
     if (warp == 0) tc_alloc(&tmem_base_s, 512u);
@@ -227,6 +268,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         if (lane == 0) {
             const unsigned win_tx = (unsigned)(g.np_load * g.load_rows * 16);
             unsigned P = 0;
+            WSP_DECL
             unsigned pi = atomicAdd(a.counter, 1u);
             while ((long long)pi < a.n) {
                 const long long pt = a.order ? (long long)a.order[pi] : (long long)pi;
@@ -246,7 +288,9 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     a.tail_recs[pi].pt = -1;
                 } else {
                     const unsigned ws = P % WS_NWIN;
-                    if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u);
+                    WSP(0)
+                    if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u, __LINE__);
+                    WSP(1)
                     WsPoint &e = ent[P & (WS_NENT - 1)];
                     e.c1 = c1; e.r1 = r1; e.pt = pt; e.pi = (long long)pi;
                     e.x0 = (int)x0; e.y0 = (int)y0; e.W = W; e.H = H; e.done = 0;
@@ -259,9 +303,11 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 pi = pi_next;
             }
             const unsigned ws = P % WS_NWIN;
-            if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u);
+            if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u, __LINE__);
             ent[P & (WS_NENT - 1)].done = 1;
             ws_arrive(BAR(&B.win_full[ws]));
+            WSP(0)
+            WSP_OUT(0)
         }
     } else if (warp < WS_W_GATHER) {
         // ================================================================ mma issuers (x block w each)
@@ -270,9 +316,13 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             unsigned P = 0, round = 0, use0 = 0, use1 = 0;
             int slot = 0;
             const uint64_t adesc0 = tc_smem_desc(smem_u32(sA), (uint32_t)g.lbo_a, 128u);
+            uint64_t ad = adesc0;
+            WSP_DECL
             for (;;) {
                 const unsigned ws = P % WS_NWIN;
-                ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u);
+                WSP(0)
+                ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
+                WSP(1)
                 const WsPoint &e = ent[P & (WS_NENT - 1)];
                 if (e.done) break;
                 const int RH = e.H - s + 1, RW = e.W - s + 1, xoff = e.x0 & 15;
@@ -282,22 +332,32 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 const unsigned set = P & 1u;
                 const uint32_t dcol = tbase + set * WS_ACC_COLS + (uint32_t)(w * 64);
                 const uint64_t bdesc0 = tc_smem_desc(smem_u32(sWin + (size_t)ws * g.win_bytes + (size_t)w * PS), (uint32_t)PS, 128u);
+                const uint32_t b_slot_full = bar0 + (uint32_t)offsetof(WsBars, slot_full);
+                const uint32_t b_slot_empty = bar0 + (uint32_t)offsetof(WsBars, slot_empty);
+                const uint64_t a_step = (uint64_t)(g.slot_bytes >> 4), a_kk = (uint64_t)((2 * g.lbo_a) >> 4), b_kk = (uint64_t)((2 * PS) >> 4);
+                const bool mine = w < nxq;
                 for (int b = 0; b < nbatch; ++b) {
                     const unsigned use = set ? use1 : use0;
-                    if (use >= 1u) ws_wait(BAR(&B.acc_empty[set]), (use - 1u) & 1u);
+                    WSP(0)
+                    if (use >= 1u) ws_wait(BAR(&B.acc_empty[set]), (use - 1u) & 1u, __LINE__);
+                    WSP(2)
                     tc_fence_after();
+                    uint64_t bd = bdesc0;
+                    uint32_t accum = 0u;
                     for (int pr = 0; pr < g.npairs; ++pr) {
-                        ws_wait(BAR(&B.slot_full[slot]), round);
+                        ws_wait(b_slot_full + 8u * (uint32_t)slot, round, __LINE__);
+                        WSP(3)
                         tc_fence_after();
-                        if (w < nxq) {
-                            const uint64_t ad = adesc0 + (uint64_t)((slot * g.slot_bytes) >> 4);
-                            const uint64_t bd = bdesc0 + (uint64_t)(2 * pr);
-                            for (int kk = 0; kk < g.ks; ++kk)
-                                tc_mma_i8_ss(dcol, ad + (uint64_t)((kk * 2 * g.lbo_a) >> 4), bd + (uint64_t)((kk * 2 * PS) >> 4), idesc,
-                                             (pr | kk) ? 1u : 0u);
+                        if (mine) {
+                            tc_mma_i8_ss(dcol, ad, bd, idesc, accum);
+                            for (int kk = 1; kk < g.ks; ++kk)
+                                tc_mma_i8_ss(dcol, ad + (uint64_t)kk * a_kk, bd + (uint64_t)kk * b_kk, idesc, 1u);
                         }
-                        tc_commit_addr(BAR(&B.slot_empty[slot]));
-                        if (++slot == g.nslots) { slot = 0; round ^= 1u; }
+                        accum = 1u;
+                        bd += 2;
+                        tc_commit_addr(b_slot_empty + 8u * (uint32_t)slot);
+                        ad += a_step;
+                        if (++slot == g.nslots) { slot = 0; round ^= 1u; ad = adesc0; }
                     }
                     tc_commit_addr(BAR(&B.acc_full[set]));
                     if (set) ++use1; else ++use0;
@@ -305,6 +365,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 tc_commit_addr(BAR(&B.win_empty[ws]));
                 ++P;
             }
+            if (w == 0) WSP_OUT(1)
             if (w == 0) {
                 total_pts_s[0] = (P + 1u) / 2u; total_pts_s[1] = P / 2u;
                 __threadfence_block();
@@ -312,25 +373,45 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 __threadfence_block();
             }
             // poison completion of both accumulator barriers (the epilogue groups leave on it)
-            if (use0 >= 1u) ws_wait(BAR(&B.acc_empty[0]), (use0 - 1u) & 1u);
+            if (use0 >= 1u) ws_wait(BAR(&B.acc_empty[0]), (use0 - 1u) & 1u, __LINE__);
             ws_arrive(BAR(&B.acc_full[0]));
-            if (use1 >= 1u) ws_wait(BAR(&B.acc_empty[1]), (use1 - 1u) & 1u);
+            if (use1 >= 1u) ws_wait(BAR(&B.acc_empty[1]), (use1 - 1u) & 1u, __LINE__);
             ws_arrive(BAR(&B.acc_full[1]));
         }
     } else if (warp < WS_W_STATS) {
         // ================================================================ gather + Toeplitz expansion
         const int gt = tid - WS_W_GATHER * 32, gw = warp - WS_W_GATHER;
         const int nwords = g.nwords, tw = g.tw;
-        const int rows_per_pass = 128 / nwords;
+        const int rows_per_pass = (32 * WS_NG) / nwords;
         const int gi = gt / nwords, wj = gt - gi * nwords;
         const bool active = gi < rows_per_pass;
         double djv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) djv[k] = (double)min(4 * wj + k, s - 1);     // columns past the row repeat the last one (discarded)
-        unsigned P = 0, J = 0, q = 0;
+        // expansion tasks of this lane (two per row pair; task -> (angle, row parity, word) never changes)
+        int ex_src[2], ex_ip[2], ex_dst[2][4];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int t = lane + 32 * it;
+            const int rest = t / (nwords + 1), wjj = t - rest * (nwords + 1);
+            const int ai = rest >> 1, ip = rest & 1;
+            ex_ip[it] = ip;
+            ex_src[it] = (ai * s + ip) * tw + wjj;
+#pragma unroll
+            for (int ee = 0; ee < 4; ++ee) {
+                const int wq = wjj + ee;
+                ex_dst[it][ee] = (2 * ai + ip) * 16 + (wq >> 2) * g.lbo_a + (wq & 3) * 4 + ee * 512;
+            }
+        }
+        unsigned P = 0, J = 0;
+        int qslot = 0;                    // slot of the job's first row pair
+        unsigned quse = 0;                // ... and how often that slot has been used before
+        WSP_DECL
         for (;;) {
             const unsigned ws = P % WS_NWIN;
-            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u);
+            WSP(0)
+            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
+            WSP(1)
             const WsPoint &e = ent[P & (WS_NENT - 1)];
             if (e.done) break;
             const double c1 = e.c1, r1 = e.r1;
@@ -347,50 +428,92 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     if (template_inside_warp(a.rows1, a.cols1, __dsub_rn(r1, tab[2]), __dsub_rn(c1, tab[3]), tab[0], tab[1], s))
                         inside_mask |= 1u << ai;
                 }
+                const bool all_fast = a.rot_order == 0 && inside_mask == (1u << nb) - 1u;
+                WSD(50)
+                uint32_t ls0 = 0, ls1 = 0, ls2 = 0, lq0 = 0, lq1 = 0, lq2 = 0;
+                int lzero = 0;
+                auto account = [&](int ai, uint32_t word, int nvalid) {
+                    // sums over the valid bytes of the word (the others are 0); zero test on the valid bytes only
+                    const uint32_t sm_ = __dp4a(word, 0x01010101u, 0u), sq_ = __dp4a(word, word, 0u);
+                    ls0 += ai == 0 ? sm_ : 0u; ls1 += ai == 1 ? sm_ : 0u; ls2 += ai == 2 ? sm_ : 0u;
+                    lq0 += ai == 0 ? sq_ : 0u; lq1 += ai == 1 ? sq_ : 0u; lq2 += ai == 2 ? sq_ : 0u;
+                    const uint32_t filled = nvalid >= 4 ? word : (word | (0xffffffffu << (8 * nvalid)));
+                    // a zero byte among the valid ones: (x - 0x01010101) & ~x & 0x80808080
+                    lzero |= (((filled - 0x01010101u) & ~filled & 0x80808080u) != 0u);
+                };
                 if (active) {
-                    uint32_t lsum = 0, lsq = 0;
-                    int lzero = 0, cur_a = -1;
-                    for (int R = gi; R < nb * s; R += rows_per_pass) {
-                        const int ai = (R >= s) + (R >= 2 * s), i = R - ai * s;
-                        if (ai != cur_a) {
-                            if (cur_a >= 0) { atomicAdd(&tr.tsum[cur_a], lsum); atomicAdd(&tr.tsq[cur_a], lsq); }
-                            lsum = 0; lsq = 0; cur_a = ai;
-                        }
-                        const double *tab = a.tab + 4 * (a0 + ai);
-                        const double cs = tab[0], sn = tab[1];
-                        const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
-                        const double di = (double)i;
-                        const double br = __dadd_rn(off0, __dmul_rn(di, cs));
-                        const double bc = __dadd_rn(off1, __dmul_rn(di, -sn));
-                        const bool inside = (inside_mask >> ai) & 1u;
-                        uint32_t word = 0;
-                        if (inside && a.rot_order == 0) {
-                            uint32_t v[4];
+                    const int nrow = nb * s;
+                    const int nvalid = min(4, s - 4 * wj);
+                    if (all_fast) {
+                        // four tasks (16 pixels) per step: all loads are in flight before the first is used
+                        for (int R0 = gi; R0 < nrow; R0 += 4 * rows_per_pass) {
+                            uint32_t v[4][4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const double row = __dadd_rn(br, __dmul_rn(djv[k], sn));
-                                const double col = __dadd_rn(bc, __dmul_rn(djv[k], cs));
-                                v[k] = template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0);
-                            }
+                            for (int u = 0; u < 4; ++u) {
+                                const int R = min(R0 + u * rows_per_pass, nrow - 1);
+                                const int ai = (R >= s) + (R >= 2 * s), i = R - ai * s;
+                                const double *tab = a.tab + 4 * (a0 + ai);
+                                const double cs = tab[0], sn = tab[1];
+                                const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
+                                const double di = (double)i;
+                                const double br = __dadd_rn(off0, __dmul_rn(di, cs));
+                                const double bc = __dadd_rn(off1, __dmul_rn(di, -sn));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (4 * wj + k < s) { word |= v[k] << (8 * k); lsum += v[k]; lsq += v[k] * v[k]; lzero |= (v[k] == 0u); }
-                        } else {
-#pragma unroll 1
-                            for (int k = 0; k < 4; ++k) {
-                                if (4 * wj + k < s) {
+                                for (int k = 0; k < 4; ++k) {
                                     const double row = __dadd_rn(br, __dmul_rn(djv[k], sn));
                                     const double col = __dadd_rn(bc, __dmul_rn(djv[k], cs));
-                                    const uint32_t v = inside ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order)
-                                                              : template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order);
-                                    word |= v << (8 * k); lsum += v; lsq += v * v; lzero |= (v == 0u);
+                                    v[u][k] = template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0);
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int R = R0 + u * rows_per_pass;
+                                if (R < nrow) {
+                                    const int ai = (R >= s) + (R >= 2 * s), i = R - ai * s;
+                                    uint32_t word = v[u][0];
+                                    if (nvalid > 1) word |= v[u][1] << 8;
+                                    if (nvalid > 2) word |= v[u][2] << 16;
+                                    if (nvalid > 3) word |= v[u][3] << 24;
+                                    account(ai, word, nvalid);
+                                    buf[(ai * s + i) * tw + 1 + wj] = word;
                                 }
                             }
                         }
-                        buf[(ai * s + i) * tw + 1 + wj] = word;
+                    } else {
+                        for (int R = gi; R < nrow; R += rows_per_pass) {
+                            const int ai = (R >= s) + (R >= 2 * s), i = R - ai * s;
+                            const double *tab = a.tab + 4 * (a0 + ai);
+                            const double cs = tab[0], sn = tab[1];
+                            const double off0 = __dsub_rn(r1, tab[2]), off1 = __dsub_rn(c1, tab[3]);
+                            const double di = (double)i;
+                            const double br = __dadd_rn(off0, __dmul_rn(di, cs));
+                            const double bc = __dadd_rn(off1, __dmul_rn(di, -sn));
+                            const bool inside = (inside_mask >> ai) & 1u;
+                            uint32_t word = 0;
+#pragma unroll 1
+                            for (int k = 0; k < nvalid; ++k) {
+                                const double row = __dadd_rn(br, __dmul_rn(djv[k], sn));
+                                const double col = __dadd_rn(bc, __dmul_rn(djv[k], cs));
+                                const uint32_t v = inside ? template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order)
+                                                          : template_sample<true>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, a.rot_order);
+                                word |= v << (8 * k);
+                            }
+                            account(ai, word, nvalid);
+                            buf[(ai * s + i) * tw + 1 + wj] = word;
+                        }
                     }
-                    if (cur_a >= 0) { atomicAdd(&tr.tsum[cur_a], lsum); atomicAdd(&tr.tsq[cur_a], lsq); }
-                    if (lzero) tr.zero = 1;
+                }
+                {   // template sums: one shared-memory atomic per warp, angle and quantity
+                    ls0 = __reduce_add_sync(0xffffffffu, ls0); lq0 = __reduce_add_sync(0xffffffffu, lq0);
+                    if (nb > 1) { ls1 = __reduce_add_sync(0xffffffffu, ls1); lq1 = __reduce_add_sync(0xffffffffu, lq1); }
+                    if (nb > 2) { ls2 = __reduce_add_sync(0xffffffffu, ls2); lq2 = __reduce_add_sync(0xffffffffu, lq2); }
+                    lzero = __any_sync(0xffffffffu, lzero);
+                    if (lane == 0) {
+                        atomicAdd(&tr.tsum[0], ls0); atomicAdd(&tr.tsq[0], lq0);
+                        if (nb > 1) { atomicAdd(&tr.tsum[1], ls1); atomicAdd(&tr.tsq[1], lq1); }
+                        if (nb > 2) { atomicAdd(&tr.tsum[2], ls2); atomicAdd(&tr.tsq[2], lq2); }
+                        if (lzero) tr.zero = 1;
+                    }
                 }
                 if (gt == 0) { tr.pt = e_pt; tr.pi = e_pi; tr.x0 = e_x0; tr.W = e_W; tr.H = e_H; }
                 if (gt == 32) {          // clear the record of the next job (nobody reads it any more)
@@ -398,16 +521,41 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     nx.zero = 0;
                     for (int k = 0; k < 3; ++k) { nx.tsum[k] = 0u; nx.tsq[k] = 0u; }
                 }
-                ws_bar(1, 128);
+                WSP(2)
+                WSD(100)
+                ws_bar(1, 32 * WS_NG);
+                WSD(101)
+                WSP(3)
                 if (lane == 0) ws_arrive(BAR(&B.tpl_full[J & (WS_NENT - 1)]));
                 // ---- expansion: row pair pr -> A slot (q + pr) % nslots
                 const int ntask = 2 * nb * (nwords + 1);
-                for (int pr = gw; pr < g.npairs; pr += 4) {
-                    const unsigned qq = q + (unsigned)pr;
-                    const unsigned use = qq / (unsigned)g.nslots, slot = qq - use * (unsigned)g.nslots;
-                    if (use >= 1u) ws_wait(BAR(&B.slot_empty[slot]), (use - 1u) & 1u);
+                for (int pr = gw; pr < g.npairs; pr += WS_NG) {
+                    int slot = qslot + pr;
+                    unsigned use = quse;
+                    while (slot >= g.nslots) { slot -= g.nslots; ++use; }
+                    WSD(200 + pr)
+                    WSP(4)
+                    if (use >= 1u) ws_wait(bar0 + (uint32_t)offsetof(WsBars, slot_empty) + 8u * (uint32_t)slot, (use - 1u) & 1u, __LINE__);
+                    WSP(5)
                     uint8_t *sl = sA + (size_t)slot * g.slot_bytes;
-                    for (int t = lane; t < ntask; t += 32) {
+                    const uint32_t *bp = buf + 2 * pr * tw;
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        if (lane + 32 * it < ntask) {
+                            uint32_t wlo = 0, whi = 0;
+                            if (2 * pr + ex_ip[it] < s) { wlo = bp[ex_src[it]]; whi = bp[ex_src[it] + 1]; }
+                            const uint32_t f1 = __byte_perm(wlo, whi, 0x6543), f2 = __byte_perm(wlo, whi, 0x5432), f3 = __byte_perm(wlo, whi, 0x4321);
+#pragma unroll
+                            for (int ee = 0; ee < 4; ++ee) {
+                                uint8_t *pw = sl + ex_dst[it][ee];
+                                *reinterpret_cast<uint32_t *>(pw) = whi;
+                                *reinterpret_cast<uint32_t *>(pw + 128) = f1;
+                                *reinterpret_cast<uint32_t *>(pw + 256) = f2;
+                                *reinterpret_cast<uint32_t *>(pw + 384) = f3;
+                            }
+                        }
+                    }
+                    for (int t = lane + 64; t < ntask; t += 32) {           // wide templates: more than 64 tasks per pair
                         const int rest = (int)__umulhi((unsigned)t, g.inv_nw1);
                         const int wjj = t - rest * (nwords + 1);
                         const int ai = rest >> 1, ip = rest & 1;
@@ -431,14 +579,20 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                             for (int c = 0; c < 4; ++c) *reinterpret_cast<uint32_t *>(pw + c * 128) = f[c];
                         }
                     }
+                    WSD(300 + pr)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) ws_arrive(BAR(&B.slot_full[slot]));
+                    if (lane == 0) ws_arrive(bar0 + (uint32_t)offsetof(WsBars, slot_full) + 8u * (uint32_t)slot);
+                    WSD(400 + pr)
                 }
-                q += (unsigned)g.npairs;
+                WSD(500)
+                qslot += g.npairs;
+                while (qslot >= g.nslots) { qslot -= g.nslots; ++quse; }
+                WSP(4)
             }
             ++P;
         }
+        if (gt == 0) WSP_OUT(2)
     } else if (warp < WS_W_EPI) {
         // ================================================================ window statistics
         const int st_ = tid - WS_W_STATS * 32;
@@ -446,39 +600,55 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         uint32_t *hqT = hsT + g.hs_words;
         const int hp = g.hp;
         unsigned P = 0;
+        WSP_DECL
         for (;;) {
             const unsigned ws = P % WS_NWIN;
-            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u);
+            WSP(0)
+            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
+            WSP(1)
             const WsPoint &e = ent[P & (WS_NENT - 1)];
             if (e.done) break;
             const int W = e.W, H = e.H, xoff = e.x0 & 15;
             const int RH = H - s + 1, RW = W - s + 1;
             const unsigned set = P & 1u;
-            if (P >= 2u) ws_wait(BAR(&B.stats_empty[set]), ((P >> 1) - 1u) & 1u);
+            if (P >= 2u) ws_wait(BAR(&B.stats_empty[set]), ((P >> 1) - 1u) & 1u, __LINE__);
+            WSP(2)
             double *wden = reinterpret_cast<double *>(ws_smem + g.off_stat + (size_t)set * g.stat_bytes);
             uint32_t *wsum = reinterpret_cast<uint32_t *>(wden + a.max_rr);
             const uint8_t *win = sWin + (size_t)ws * g.win_bytes;
-            // horizontal sliding sums, one window row per thread
-            for (int r = st_; r < H; r += 128) {
-                const uint8_t *rowp = win + 16 * r;
-                auto wb = [&](int k) -> uint32_t { const int kk = k + xoff; return rowp[(kk >> 4) * PS + (kk & 15)]; };
-                uint32_t sum = 0, sq = 0;
-                for (int j = 0; j < s; ++j) { const uint32_t v = wb(j); sum += v; sq += v * v; }
-                for (int x = 0; x < RW; ++x) {
-                    hsT[x * hp + r] = sum; hqT[x * hp + r] = sq;
-                    const uint32_t va = wb(x), vb = wb(x + s);       // x + s <= W: the staged panels hold that column
-                    sum += vb - va; sq += vb * vb - va * va;
+            // horizontal sliding sums: one (window row, x segment) per thread
+            {
+                int nsegx = WS_NST / H;
+                if (nsegx < 1) nsegx = 1;
+                if (nsegx > 4) nsegx = 4;
+                const int Lx = (RW + nsegx - 1) / nsegx;
+                for (int t = st_; t < H * nsegx; t += WS_NST) {
+                    const int sg = t / H, r = t - sg * H;
+                    const int xs = sg * Lx, xe = min(RW, xs + Lx);
+                    if (xs >= xe) continue;
+                    const uint8_t *rowp = win + 16 * r;
+                    auto wb = [&](int k) -> uint32_t { const int kk = k + xoff; return rowp[(kk >> 4) * PS + (kk & 15)]; };
+                    uint32_t sum = 0, sq = 0;
+                    for (int j = 0; j < s; ++j) { const uint32_t v = wb(xs + j); sum += v; sq += v * v; }
+                    for (int x = xs; x < xe; ++x) {
+                        hsT[x * hp + r] = sum; hqT[x * hp + r] = sq;
+                        const uint32_t va = wb(x), vb = wb(x + s);       // x + s <= W: the staged panels hold that column
+                        sum += vb - va; sq += vb * vb - va * va;
+                    }
                 }
             }
-            ws_bar(2, 128);
+            WSP(3)
+            ws_bar(2, WS_NST);
+            WSP(4)
             if (lane == 0) ws_arrive(BAR(&B.win_empty[ws]));        // this warp is done with the window
-            // vertical sliding sums -> window sum and denominator per displacement
+            // vertical sliding sums -> window sum / sum of squares per displacement
+            uint32_t *wsq = wsum + a.max_rr;                          // later overwritten by 1 / wden (float), element by element
             {
-                int nseg = 128 / RW;
+                int nseg = WS_NST / RW;
                 if (nseg < 1) nseg = 1;
                 if (nseg > RH) nseg = RH;
                 const int L = (RH + nseg - 1) / nseg;
-                for (int t = st_; t < RW * nseg; t += 128) {
+                for (int t = st_; t < RW * nseg; t += WS_NST) {
                     const int sg = t / RW, x = t - sg * RW;
                     const int ys = sg * L, ye = min(RH, ys + L);
                     if (ys >= ye) continue;
@@ -487,16 +657,45 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     for (int i = 0; i < s; ++i) { sum += hs[ys + i]; sq += hq[ys + i]; }
                     for (int y = ys; y < ye; ++y) {
                         wsum[y * RW + x] = sum;
-                        wden[y * RW + x] = window_den(sum, sq, a.inv_area);
+                        wsq[y * RW + x] = sq;
                         if (y + 1 < ye) { sum += hs[y + s] - hs[y]; sq += hq[y + s] - hq[y]; }
                     }
                 }
             }
+            WSP(5)
+            ws_bar(2, WS_NST);                                          // hsT / hqT are free again; sums visible to the group
+            WSP(4)
+            // denominators: four independent FP64 chains per thread
+            {
+                const int RR = RH * RW;
+                float *inv = reinterpret_cast<float *>(wsq);
+                for (int base = 0; base < RR; base += 4 * WS_NST) {
+                    double d[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int idx = min(base + WS_NST * c + st_, RR - 1);
+                        d[c] = window_den(wsum[idx], wsq[idx], a.inv_area);
+                    }
+                    __syncwarp();                                      // (clamped duplicates read before anybody overwrites them)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int idx = base + WS_NST * c + st_;
+                        if (idx < RR) {
+                            wden[idx] = d[c];
+                            const float wd = (float)d[c];
+                            float iv;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iv) : "f"(wd));
+                            inv[idx] = wd > 0.0f ? iv : 0.0f;
+                        }
+                    }
+                }
+            }
+            WSP(6)
             __syncwarp();
             if (lane == 0) ws_arrive(BAR(&B.stats_full[set]));
-            ws_bar(2, 128);                                          // hsT / hqT are free again
             ++P;
         }
+        if (st_ == 0) WSP_OUT(3)
     } else {
         // ================================================================ epilogue groups (points P = e, e + 2, ...)
         const int eg = (warp - WS_W_EPI) >> 2;
@@ -508,11 +707,13 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         int32_t *C = reinterpret_cast<int32_t *>(ws_smem + g.off_c) + (size_t)eg * nab * g.cpl;
         const double *wden = reinterpret_cast<const double *>(ws_smem + g.off_stat + (size_t)eg * g.stat_bytes);
         const uint32_t *wsum = reinterpret_cast<const uint32_t *>(wden + a.max_rr);
+        const float *inv = reinterpret_cast<const float *>(wsum + a.max_rr);
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const int dx = 4 * quarter + (lane >> 3), aa = (lane >> 1) & 3, ip = lane & 1;
         const long long Nll = (long long)s * (long long)s;
         unsigned acc_use = 0, stat_use = 0;
         bool leave = false;
+        WSP_DECL
         for (unsigned n = 0; !leave; ++n) {
             const unsigned P = (unsigned)eg + 2u * n;
             float best_r = -INFINITY;
@@ -522,44 +723,45 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             int W = 0, H = 0, xoff = 0, RH = 0, RW = 0, RR = 0;
             for (int b = 0; b < nbatch; ++b) {
                 const unsigned J = P * (unsigned)nbatch + (unsigned)b;
-                ws_wait(BAR(&B.acc_full[eg]), acc_use & 1u); ++acc_use;
+                WSP(0)
+                ws_wait(BAR(&B.acc_full[eg]), acc_use & 1u, __LINE__); ++acc_use;
+                WSP(1)
                 if (b == 0 && all_done_s && n == total_pts_s[eg]) { leave = true; break; }
                 tc_fence_after();
-                ws_wait(BAR(&B.tpl_full[J & (WS_NENT - 1)]), (J >> 3) & 1u);
+                ws_wait(BAR(&B.tpl_full[J & (WS_NENT - 1)]), (J >> 3) & 1u, __LINE__);
                 const WsTplRec &tr = trec[J & (WS_NENT - 1)];
                 if (b == 0) {
                     pt = tr.pt; pi = tr.pi; W = tr.W; H = tr.H; xoff = tr.x0 & 15;
                     RH = H - s + 1; RW = W - s + 1; RR = RH * RW;
-                    ws_wait(BAR(&B.stats_full[eg]), stat_use & 1u); ++stat_use;
+                    ws_wait(BAR(&B.stats_full[eg]), stat_use & 1u, __LINE__); ++stat_use;
                 }
+                WSP(2)
                 const int a0 = b * per, nb = min(per, A_ - a0);
                 const bool zero = tr.zero != 0;
-                uint32_t tsum[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) tsum[k] = tr.tsum[k];
                 if (et < nb) E.st[et] = templ_stats(tr.tsum[et], tr.tsq[et], a.inv_area, a.sqrt_inv_area);
+                // ---- combined correlation numerators -> C[a][y * RW + x]
                 if (!invalid && !zero) {
-                    // ---- combined correlation numerators -> C[a][y * RW + x]
                     const int nxq = (xoff + RW + 15) >> 4;
                     const int n16 = (RH + 1 + 15) & ~15;
+                    const int ak = aa < nb ? aa : 0;
                     for (int xq = 0; xq < nxq; ++xq) {
                         const int xw = 16 * xq + 4 * quarter - xoff;            // first x of this warp's four dx
                         if (xw + 3 < 0 || xw >= RW) continue;                   // warp-uniform
                         const int x = 16 * xq + dx - xoff;
                         const bool lane_ok = x >= 0 && x < RW && aa < nb;
-                        int32_t *cp = C + aa * g.cpl + x;
+                        int32_t *cp = C + ak * g.cpl + (lane_ok ? x : 0) - ip * RW;     // row y = c0 + 2 t - ip
+                        const uint32_t tad = tbase + (uint32_t)eg * WS_ACC_COLS + (uint32_t)(xq * 64) + lane_base;
                         uint32_t carry = 0;
                         for (int c0 = 0; c0 < n16; c0 += 16) {
                             uint32_t r[16];
-                            tc_ld16(tbase + (uint32_t)eg * WS_ACC_COLS + (uint32_t)(xq * 64 + c0) + lane_base, r);
+                            tc_ld16(tad + (uint32_t)c0, r);
                             tc_ld_wait();
+                            const int ylo = ip - c0, yhi = RH + ip - c0;           // valid 2 t: ylo <= 2 t < yhi
 #pragma unroll
                             for (int t = 0; t < 8; ++t) {
                                 const uint32_t send = ip ? r[2 * t + 1] : (t ? r[t ? 2 * t - 1 : 0] : carry);
                                 const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                                const int y = c0 + 2 * t - ip;
-                                const uint32_t val = r[2 * t] + recv;
-                                if (lane_ok && y >= 0 && y < RH) cp[y * RW] = (int32_t)val;
+                                if (lane_ok && 2 * t >= ylo && 2 * t < yhi) cp[(c0 + 2 * t) * RW] = (int32_t)(r[2 * t] + recv);
                             }
                             carry = r[15];
                         }
@@ -569,27 +771,41 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 __syncwarp();
                 if (lane == 0) ws_arrive(BAR(&B.acc_empty[eg]));
                 if (zero) invalid = true;
+                WSP(3)
                 ws_bar(barid, 128);
+                WSP(4)
                 if (invalid) continue;
 
-                // ---- float screening: an upper estimate (error < 5e-7) of every angle's maximum
+                // ---- float screening: an estimate (error < 5e-7) of every angle's maximum.  Per angle the loop keeps
+                //      max(n64 / wden) (n64 = N corr - wsum tsum, exact); the positive factor 1 / (N templNorm) comes after.
+                //      A value beyond ~0.99 in those units may be one of OpenCV's special cases (+-1 / 0): "can be 1".
                 float m[3] = {-INFINITY, -INFINITY, -INFINITY};
-                float sc[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) sc[k] = (k < nb && !E.st[k].flat) ? (float)(1.0 / ((double)Nll * E.st[k].norm)) : 0.0f;
-                for (int idx = et; idx < RR; idx += 128) {
-                    const long long wsv = (long long)wsum[idx];
-                    const float wd = (float)wden[idx];
-                    float inv;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(wd));
+                {
+                    const int N32 = s * s;
+                    uint32_t ts[3];
+                    float lim2[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        if (k < nb) {
-                            const long long n64 = (long long)C[k * g.cpl + idx] * Nll - wsv * (long long)tsum[k];
-                            const float qv = __ll2float_rn(n64) * sc[k] * inv;
-                            float v = fabsf(qv) < 0.99999f ? qv : 1.0f;
-                            if (wd == 0.0f) v = 0.0f;
-                            m[k] = fmaxf(m[k], v);
+                        const int kk = k < nb ? k : 0;
+                        ts[k] = tr.tsum[kk];
+                        const double mean = (double)tr.tsum[kk] * a.inv_area;
+                        const double var = (double)tr.tsq[kk] * a.inv_area - mean * mean;
+                        lim2[k] = (float)(0.98 * var * (double)Nll * (double)Nll * (double)Nll);
+                    }
+                    for (int base = 0; base < RR; base += 256) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int idx = min(base + 128 * c + et, RR - 1);      // the tail repeats the last element
+                            const unsigned long long wsv = (unsigned long long)wsum[idx];
+                            const float iv = inv[idx];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                if (k < nb) {
+                                    const long long n64 = (long long)C[k * g.cpl + idx] * (long long)N32 - (long long)(wsv * (unsigned long long)ts[k]);
+                                    const float qv = __ll2float_rn(n64) * iv;
+                                    m[k] = fmaxf(m[k], qv * qv < lim2[k] ? qv : INFINITY);
+                                }
+                            }
                         }
                     }
                 }
@@ -600,13 +816,17 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
                     if (lane == 0) E.m[ew][k] = v;
                 }
+                WSP(5)
                 ws_bar(barid, 128);
+                WSP(4)
                 float M[3], Mx = -INFINITY;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    M[k] = fmaxf(fmaxf(E.m[0][k], E.m[1][k]), fmaxf(E.m[2][k], E.m[3][k]));
-                    if (k < nb && E.st[k].flat) M[k] = 1.0f;
-                    if (k >= nb) M[k] = -INFINITY;
+                    const float sc = (k < nb && !E.st[k].flat) ? (float)(1.0 / ((double)Nll * E.st[k].norm)) : 0.0f;
+                    float v = fmaxf(fmaxf(E.m[0][k], E.m[1][k]), fmaxf(E.m[2][k], E.m[3][k])) * sc;
+                    if (!(v < 0.99999f)) v = 1.0f;
+                    if (k < nb && E.st[k].flat) v = 1.0f;
+                    M[k] = k < nb ? v : -INFINITY;
                     Mx = fmaxf(Mx, M[k]);
                 }
                 const float thr = fmaxf(Mx, best_r) - WS_MARGIN;
@@ -642,9 +862,14 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     }
                     if (pending >= 0) (void)ws_exact_pass(C + pending * g.cpl, wsum, wden, E.st[pending], RR, et, dst);
                 }
+                WSP(6)
                 ws_bar(barid, 128);          // C and E.st are free for the next batch
+                WSP(4)
             }
-            if (leave) break;
+            if (leave) {
+                if (et == 0) WSP_OUT(4 + eg)
+                break;
+            }
             __syncwarp();
             if (lane == 0) ws_arrive(BAR(&B.stats_empty[eg]));
             if (et == 0) {
