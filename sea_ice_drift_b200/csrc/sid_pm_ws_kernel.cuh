@@ -39,6 +39,7 @@ namespace sid {
 constexpr int WS_THREADS = 896;           // 28 warps: control | 4 mma | 8 gather | 7 stats | 2 x 4 epilogue
 constexpr int WS_W_MMA = 1, WS_W_GATHER = 5, WS_W_STATS = 13, WS_W_EPI = 20;
 constexpr int WS_NST = 7 * 32;            // stats threads
+constexpr int WS_NSTAT = 3;               // sets of window statistics (stats warps run up to 3 points ahead of the epilogue)
 constexpr int WS_NG = 8;                  // gather warps
 constexpr int WS_NWIN = 3;                // window ring
 constexpr int WS_NENT = 8;                // point entries / template records
@@ -111,10 +112,10 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     g.off_tpl = (int)off; off += (size_t)2 * g.tpl_buf_words * 4;
     off = (off + 127) & ~(size_t)127;
     g.off_stat = (int)off;
-    g.stat_bytes = (max_rr * 16 + 127) & ~127;           // wden f64 | wsum u32 | 1/wden f32 (before that: the u32 sums of squares)
-    off += (size_t)2 * g.stat_bytes;
+    g.stat_bytes = (max_rr * 12 + 127) & ~127;           // wden f64 (its low words first hold the u32 sums of squares) | wsum u32
+    off += (size_t)WS_NSTAT * g.stat_bytes;
     g.hs_words = Rmax * g.hp;
-    g.off_hs = (int)off; off += (size_t)2 * g.hs_words * 4;
+    g.off_hs = (int)off; off += (size_t)g.hs_words * 6;       // hq u32 | hs u16
     off = (off + 127) & ~(size_t)127;
     g.off_c = (int)off; off += (size_t)2 * g.nab * g.cpl * 4;
     g.smem_bytes = (int)((off + 127) & ~(size_t)127);
@@ -128,7 +129,7 @@ struct WsBars {
     unsigned long long slot_full[WS_MAX_SLOTS], slot_empty[WS_MAX_SLOTS];
     unsigned long long acc_full[2], acc_empty[2];
     unsigned long long tpl_full[WS_NENT];
-    unsigned long long stats_full[2], stats_empty[2];
+    unsigned long long stats_full[WS_NSTAT], stats_empty[WS_NSTAT];
 };
 struct WsEpi { TemplStats st[3]; float m[4][3]; unsigned long long key[4]; };
 
@@ -251,8 +252,8 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         for (int i = 0; i < WS_MAX_SLOTS; ++i) { mbar_init(&B.slot_full[i], 1); mbar_init(&B.slot_empty[i], 4); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&B.acc_full[i], 4); mbar_init(&B.acc_empty[i], 4);
-            mbar_init(&B.stats_full[i], WS_NST / 32); mbar_init(&B.stats_empty[i], 4);
         }
+        for (int i = 0; i < WS_NSTAT; ++i) { mbar_init(&B.stats_full[i], WS_NST / 32); mbar_init(&B.stats_empty[i], 4); }
         for (int i = 0; i < WS_NENT; ++i) mbar_init(&B.tpl_full[i], WS_NG);
         all_done_s = 0; total_pts_s[0] = 0u; total_pts_s[1] = 0u;
     }
@@ -580,9 +581,11 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                         }
                     }
                     WSD(300 + pr)
+                    WSP(6)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) ws_arrive(bar0 + (uint32_t)offsetof(WsBars, slot_full) + 8u * (uint32_t)slot);
+                    WSP(7)
                     WSD(400 + pr)
                 }
                 WSD(500)
@@ -596,8 +599,8 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
     } else if (warp < WS_W_EPI) {
         // ================================================================ window statistics
         const int st_ = tid - WS_W_STATS * 32;
-        uint32_t *hsT = reinterpret_cast<uint32_t *>(ws_smem + g.off_hs);
-        uint32_t *hqT = hsT + g.hs_words;
+        uint32_t *hqT = reinterpret_cast<uint32_t *>(ws_smem + g.off_hs);
+        uint16_t *hsT = reinterpret_cast<uint16_t *>(hqT + g.hs_words);        // a row sum of s bytes fits 16 bits (s <= 112)
         const int hp = g.hp;
         unsigned P = 0;
         WSP_DECL
@@ -610,8 +613,8 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             if (e.done) break;
             const int W = e.W, H = e.H, xoff = e.x0 & 15;
             const int RH = H - s + 1, RW = W - s + 1;
-            const unsigned set = P & 1u;
-            if (P >= 2u) ws_wait(BAR(&B.stats_empty[set]), ((P >> 1) - 1u) & 1u, __LINE__);
+            const unsigned set = P % WS_NSTAT;
+            if (P >= WS_NSTAT) ws_wait(BAR(&B.stats_empty[set]), ((P / WS_NSTAT) - 1u) & 1u, __LINE__);
             WSP(2)
             double *wden = reinterpret_cast<double *>(ws_smem + g.off_stat + (size_t)set * g.stat_bytes);
             uint32_t *wsum = reinterpret_cast<uint32_t *>(wden + a.max_rr);
@@ -631,7 +634,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     uint32_t sum = 0, sq = 0;
                     for (int j = 0; j < s; ++j) { const uint32_t v = wb(xs + j); sum += v; sq += v * v; }
                     for (int x = xs; x < xe; ++x) {
-                        hsT[x * hp + r] = sum; hqT[x * hp + r] = sq;
+                        hsT[x * hp + r] = (uint16_t)sum; hqT[x * hp + r] = sq;
                         const uint32_t va = wb(x), vb = wb(x + s);       // x + s <= W: the staged panels hold that column
                         sum += vb - va; sq += vb * vb - va * va;
                     }
@@ -642,7 +645,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             WSP(4)
             if (lane == 0) ws_arrive(BAR(&B.win_empty[ws]));        // this warp is done with the window
             // vertical sliding sums -> window sum / sum of squares per displacement
-            uint32_t *wsq = wsum + a.max_rr;                          // later overwritten by 1 / wden (float), element by element
+            uint32_t *wsq2 = reinterpret_cast<uint32_t *>(wden);       // sums of squares in the low word of each wden slot (overwritten in place)
             {
                 int nseg = WS_NST / RW;
                 if (nseg < 1) nseg = 1;
@@ -652,13 +655,13 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     const int sg = t / RW, x = t - sg * RW;
                     const int ys = sg * L, ye = min(RH, ys + L);
                     if (ys >= ye) continue;
-                    const uint32_t *hs = hsT + x * hp, *hq = hqT + x * hp;
+                    const uint16_t *hs = hsT + x * hp; const uint32_t *hq = hqT + x * hp;
                     uint32_t sum = 0, sq = 0;
                     for (int i = 0; i < s; ++i) { sum += hs[ys + i]; sq += hq[ys + i]; }
                     for (int y = ys; y < ye; ++y) {
                         wsum[y * RW + x] = sum;
-                        wsq[y * RW + x] = sq;
-                        if (y + 1 < ye) { sum += hs[y + s] - hs[y]; sq += hq[y + s] - hq[y]; }
+                        wsq2[2 * (y * RW + x)] = sq;
+                        if (y + 1 < ye) { sum += (uint32_t)hs[y + s] - (uint32_t)hs[y]; sq += hq[y + s] - hq[y]; }
                     }
                 }
             }
@@ -668,25 +671,17 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             // denominators: four independent FP64 chains per thread
             {
                 const int RR = RH * RW;
-                float *inv = reinterpret_cast<float *>(wsq);
                 for (int base = 0; base < RR; base += 4 * WS_NST) {
                     double d[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int idx = min(base + WS_NST * c + st_, RR - 1);
-                        d[c] = window_den(wsum[idx], wsq[idx], a.inv_area);
+                        d[c] = window_den(wsum[idx], wsq2[2 * idx], a.inv_area);
                     }
-                    __syncwarp();                                      // (clamped duplicates read before anybody overwrites them)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int idx = base + WS_NST * c + st_;
-                        if (idx < RR) {
-                            wden[idx] = d[c];
-                            const float wd = (float)d[c];
-                            float iv;
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iv) : "f"(wd));
-                            inv[idx] = wd > 0.0f ? iv : 0.0f;
-                        }
+                        if (idx < RR) wden[idx] = d[c];
                     }
                 }
             }
@@ -705,17 +700,17 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         const int barid = 3 + eg;
         WsEpi &E = epi[eg];
         int32_t *C = reinterpret_cast<int32_t *>(ws_smem + g.off_c) + (size_t)eg * nab * g.cpl;
-        const double *wden = reinterpret_cast<const double *>(ws_smem + g.off_stat + (size_t)eg * g.stat_bytes);
-        const uint32_t *wsum = reinterpret_cast<const uint32_t *>(wden + a.max_rr);
-        const float *inv = reinterpret_cast<const float *>(wsum + a.max_rr);
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const int dx = 4 * quarter + (lane >> 3), aa = (lane >> 1) & 3, ip = lane & 1;
         const long long Nll = (long long)s * (long long)s;
-        unsigned acc_use = 0, stat_use = 0;
+        unsigned acc_use = 0;
         bool leave = false;
         WSP_DECL
         for (unsigned n = 0; !leave; ++n) {
             const unsigned P = (unsigned)eg + 2u * n;
+            const unsigned sset = P % WS_NSTAT;
+            const double *wden = reinterpret_cast<const double *>(ws_smem + g.off_stat + (size_t)sset * g.stat_bytes);
+            const uint32_t *wsum = reinterpret_cast<const uint32_t *>(wden + a.max_rr);
             float best_r = -INFINITY;
             int best_a = -1, best_idx = 0;
             bool invalid = false;
@@ -733,7 +728,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 if (b == 0) {
                     pt = tr.pt; pi = tr.pi; W = tr.W; H = tr.H; xoff = tr.x0 & 15;
                     RH = H - s + 1; RW = W - s + 1; RR = RH * RW;
-                    ws_wait(BAR(&B.stats_full[eg]), stat_use & 1u, __LINE__); ++stat_use;
+                    ws_wait(BAR(&B.stats_full[sset]), (P / WS_NSTAT) & 1u, __LINE__);
                 }
                 WSP(2)
                 const int a0 = b * per, nb = min(per, A_ - a0);
@@ -781,28 +776,28 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 //      A value beyond ~0.99 in those units may be one of OpenCV's special cases (+-1 / 0): "can be 1".
                 float m[3] = {-INFINITY, -INFINITY, -INFINITY};
                 {
-                    const int N32 = s * s;
-                    uint32_t ts[3];
+                    double mean[3];
                     float lim2[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const int kk = k < nb ? k : 0;
-                        ts[k] = tr.tsum[kk];
-                        const double mean = (double)tr.tsum[kk] * a.inv_area;
-                        const double var = (double)tr.tsq[kk] * a.inv_area - mean * mean;
-                        lim2[k] = (float)(0.98 * var * (double)Nll * (double)Nll * (double)Nll);
+                        mean[k] = (double)tr.tsum[kk] * a.inv_area;
+                        const double var = (double)tr.tsq[kk] * a.inv_area - mean[k] * mean[k];
+                        lim2[k] = (float)(0.98 * var * (double)Nll);
                     }
                     for (int base = 0; base < RR; base += 256) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
                             const int idx = min(base + 128 * c + et, RR - 1);      // the tail repeats the last element
-                            const unsigned long long wsv = (unsigned long long)wsum[idx];
-                            const float iv = inv[idx];
+                            const double wsd = (double)wsum[idx];
+                            const float wd = (float)wden[idx];
+                            float iv;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iv) : "f"(wd));
+                            if (!(wd > 0.0f)) iv = 0.0f;                             // flat window: the exact value is 0
 #pragma unroll
                             for (int k = 0; k < 3; ++k) {
                                 if (k < nb) {
-                                    const long long n64 = (long long)C[k * g.cpl + idx] * (long long)N32 - (long long)(wsv * (unsigned long long)ts[k]);
-                                    const float qv = __ll2float_rn(n64) * iv;
+                                    const float qv = (float)fma(-wsd, mean[k], (double)C[k * g.cpl + idx]) * iv;
                                     m[k] = fmaxf(m[k], qv * qv < lim2[k] ? qv : INFINITY);
                                 }
                             }
@@ -822,7 +817,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 float M[3], Mx = -INFINITY;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float sc = (k < nb && !E.st[k].flat) ? (float)(1.0 / ((double)Nll * E.st[k].norm)) : 0.0f;
+                    const float sc = (k < nb && !E.st[k].flat) ? (float)(1.0 / E.st[k].norm) : 0.0f;
                     float v = fmaxf(fmaxf(E.m[0][k], E.m[1][k]), fmaxf(E.m[2][k], E.m[3][k])) * sc;
                     if (!(v < 0.99999f)) v = 1.0f;
                     if (k < nb && E.st[k].flat) v = 1.0f;
@@ -871,7 +866,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 break;
             }
             __syncwarp();
-            if (lane == 0) ws_arrive(BAR(&B.stats_empty[eg]));
+            if (lane == 0) ws_arrive(BAR(&B.stats_empty[sset]));
             if (et == 0) {
                 if (invalid || best_a < 0) {
                     double *o = a.out + 5 * pt;
