@@ -287,14 +287,12 @@ __device__ __forceinline__ void ncc_finish4(const double (&num)[4], const double
     bool redo = false;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const double an = fabs(num[c]);
         const unsigned long long low = (unsigned long long)__double_as_longlong(q[c]) & 0x1fffffffull;
         const unsigned long long d = low > 0x10000000ull ? low - 0x10000000ull : 0x10000000ull - low;
-        const bool inside = an < t[c];
-        const bool fast_ok = d > 16ull && t[c] > 1e-280 && fabs(q[c]) > 1e-30;
-        redo = redo || (inside && !fast_ok);
-        const float unit = an < __dmul_rn(t[c], 1.125) ? (num[c] > 0.0 ? 1.0f : -1.0f) : 0.0f;
-        v[c] = inside ? __double2float_rn(q[c]) : unit;
+        // anything but the plain quotient (|num| >= t: OpenCV's +-1 / 0 cases) goes through the exact path below
+        const bool fast_ok = fabs(num[c]) < t[c] && d > 16ull && t[c] > 1e-280 && fabs(q[c]) > 1e-30;
+        redo = redo || !fast_ok;
+        v[c] = __double2float_rn(q[c]);
     }
     if (redo) {
 #pragma unroll

@@ -150,16 +150,18 @@ __device__ __forceinline__ void ws_wait(uint32_t bar, unsigned parity, int line 
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000000u) : "memory");
     if (ok) return;
     const long long t0 = clock64();
+    unsigned it = 0;
     for (;;) {
+        __nanosleep(40);                    // the hardware suspend is short (~100 clk): keep the re-polling off the issue slots
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000000u) : "memory");
         if (ok) return;
+        if ((++it & 255u) != 0u) continue;
 #ifdef SID_WS_DEBUG
         if (*(volatile int *)&g_ws_abort[blockIdx.x] || clock64() - t0 > 100000000LL) {
             if ((threadIdx.x & 31) == 0 && blockIdx.x == 0 && atomicAdd(&g_ws_msgs, 1) < 200)
-                printf("[ws] block %d warp %d lane %d: wait timed out, barrier byte %d parity %u line %d | gather prog %d %d %d %d %d %d %d %d\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
-                       (int)(threadIdx.x & 31), (int)(bar - g_ws_bar0), parity, line, g_ws_prog[5], g_ws_prog[6], g_ws_prog[7], g_ws_prog[8],
-                       g_ws_prog[9], g_ws_prog[10], g_ws_prog[11], g_ws_prog[12]);
+                printf("[ws] block %d warp %d lane %d: wait timed out, barrier byte %d parity %u line %d\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+                       (int)(threadIdx.x & 31), (int)(bar - g_ws_bar0), parity, line);
             __nanosleep(1000000);
             g_ws_abort[blockIdx.x] = 1;
             return;
@@ -351,8 +353,12 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                         tc_fence_after();
                         if (mine) {
                             tc_mma_i8_ss(dcol, ad, bd, idesc, accum);
-                            for (int kk = 1; kk < g.ks; ++kk)
-                                tc_mma_i8_ss(dcol, ad + (uint64_t)kk * a_kk, bd + (uint64_t)kk * b_kk, idesc, 1u);
+                            uint64_t a2 = ad, b2 = bd;
+#pragma unroll 1
+                            for (int kk = 1; kk < g.ks; ++kk) {
+                                a2 += a_kk; b2 += b_kk;
+                                tc_mma_i8_ss(dcol, a2, b2, idesc, 1u);
+                            }
                         }
                         accum = 1u;
                         bd += 2;
@@ -630,12 +636,41 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     const int xs = sg * Lx, xe = min(RW, xs + Lx);
                     if (xs >= xe) continue;
                     const uint8_t *rowp = win + 16 * r;
-                    auto wb = [&](int k) -> uint32_t { const int kk = k + xoff; return rowp[(kk >> 4) * PS + (kk & 15)]; };
+                    const int c0 = xs + xoff;                            // staged column of the segment's first window byte
+                    // the first box sum from aligned words (two dot products per word), masked at both ends
                     uint32_t sum = 0, sq = 0;
-                    for (int j = 0; j < s; ++j) { const uint32_t v = wb(xs + j); sum += v; sq += v * v; }
+                    {
+                        const int cend = c0 + s;
+                        int cw = c0 & ~3;                                // column of the current word
+                        const int q = c0 >> 2;
+                        const uint8_t *wp = rowp + (q >> 2) * PS + (q & 3) * 4;
+                        int wleft = 4 - (q & 3);                         // words left in this 16-byte panel row
+                        uint32_t mlo = 0xffffffffu << (8 * (c0 & 3));
+                        while (cw < cend) {
+                            uint32_t w = *reinterpret_cast<const uint32_t *>(wp) & mlo;
+                            const int hi = cend - cw;                    // valid bytes of this word end at byte hi (>= 1)
+                            if (hi < 4) w &= 0xffffffffu >> (8 * (4 - hi));
+                            sum = __dp4a(w, 0x01010101u, sum);
+                            sq = __dp4a(w, w, sq);
+                            mlo = 0xffffffffu;
+                            cw += 4; wp += 4;
+                            if (--wleft == 0) { wp += PS - 16; wleft = 4; }
+                        }
+                    }
+                    // two byte streams: the column leaving the box and the column entering it
+                    const uint8_t *po = rowp + (c0 >> 4) * PS + (c0 & 15);
+                    int lo_left = 16 - (c0 & 15);
+                    const int c1 = c0 + s;
+                    const uint8_t *pi_ = rowp + (c1 >> 4) * PS + (c1 & 15);
+                    int li_left = 16 - (c1 & 15);
+                    uint16_t *hsp = hsT + xs * hp + r;
+                    uint32_t *hqp = hqT + xs * hp + r;
                     for (int x = xs; x < xe; ++x) {
-                        hsT[x * hp + r] = (uint16_t)sum; hqT[x * hp + r] = sq;
-                        const uint32_t va = wb(x), vb = wb(x + s);       // x + s <= W: the staged panels hold that column
+                        *hsp = (uint16_t)sum; *hqp = sq;
+                        hsp += hp; hqp += hp;
+                        const uint32_t va = *po++, vb = *pi_++;          // x + s <= W: the staged panels hold that column
+                        if (--lo_left == 0) { po += PS - 16; lo_left = 16; }
+                        if (--li_left == 0) { pi_ += PS - 16; li_left = 16; }
                         sum += vb - va; sq += vb * vb - va * va;
                     }
                 }
