@@ -89,7 +89,7 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     g.nwords = (s + 3) / 4;
     g.tw = g.nwords + 2;
     g.ks = (g.nwords + 4 + 7) / 8;
-    g.lbo_a = 2048 + 16;
+    g.lbo_a = 2048 + 48;        // K panels 12 banks apart: the expansion's word stores of a warp spread over the banks (<= 2-way)
     g.slot_bytes = 2 * g.ks * g.lbo_a;
     g.nslots = WS_NG;          // >= the number of expanding warps: a warp's successive row pairs then reuse ONE slot, so it can never wait
                                // for a completion two phases ahead (a parity wait cannot tell phase k from phase k + 2)
@@ -142,21 +142,29 @@ __device__ int g_ws_prog[32];
 #else
 #define WSD(code) {}
 #endif
+// `ns`: back-off between polls (the hardware suspend of try_wait is only ~100 clk): long where the wait is long and not on the
+// critical path, short where a role is about to continue
+template <unsigned NS = 40u>
 __device__ __forceinline__ void ws_wait(uint32_t bar, unsigned parity, int line = 0) {
-    // try_wait SUSPENDS the thread until the phase completes or the time limit passes; with the default (short) limit the
-    // waiting warps of this kernel spent 55 % of the SM's issue slots re-polling (ncu), so ask for a long one
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000000u) : "memory");
     if (ok) return;
     const long long t0 = clock64();
-    unsigned it = 0;
     for (;;) {
-        __nanosleep(40);                    // the hardware suspend is short (~100 clk): keep the re-polling off the issue slots
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000000u) : "memory");
+        // up to 1024 polls in a 5-instruction loop, then one look at the watchdog clock
+        asm volatile("{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
+                     "WS_POLL_%=:\n\t"
+                     "nanosleep.u32 %4;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "@p bra WS_DONE_%=;\n\t"
+                     "add.u32 n, n, 1;\n\t"
+                     "setp.lt.u32 q, n, 1024;\n\t"
+                     "@q bra WS_POLL_%=;\n\t"
+                     "WS_DONE_%=:\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000000u), "r"(NS) : "memory");
         if (ok) return;
-        if ((++it & 255u) != 0u) continue;
 #ifdef SID_WS_DEBUG
         if (*(volatile int *)&g_ws_abort[blockIdx.x] || clock64() - t0 > 100000000LL) {
             if ((threadIdx.x & 31) == 0 && blockIdx.x == 0 && atomicAdd(&g_ws_msgs, 1) < 200)
@@ -292,7 +300,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 } else {
                     const unsigned ws = P % WS_NWIN;
                     WSP(0)
-                    if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u, __LINE__);
+                    if (P >= WS_NWIN) ws_wait<400u>(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u, __LINE__);
                     WSP(1)
                     WsPoint &e = ent[P & (WS_NENT - 1)];
                     e.c1 = c1; e.r1 = r1; e.pt = pt; e.pi = (long long)pi;
@@ -306,7 +314,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 pi = pi_next;
             }
             const unsigned ws = P % WS_NWIN;
-            if (P >= WS_NWIN) ws_wait(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u, __LINE__);
+            if (P >= WS_NWIN) ws_wait<400u>(BAR(&B.win_empty[ws]), ((P / WS_NWIN) - 1u) & 1u, __LINE__);
             ent[P & (WS_NENT - 1)].done = 1;
             ws_arrive(BAR(&B.win_full[ws]));
             WSP(0)
@@ -324,7 +332,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             for (;;) {
                 const unsigned ws = P % WS_NWIN;
                 WSP(0)
-                ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
+                ws_wait<100u>(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
                 WSP(1)
                 const WsPoint &e = ent[P & (WS_NENT - 1)];
                 if (e.done) break;
@@ -342,13 +350,13 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 for (int b = 0; b < nbatch; ++b) {
                     const unsigned use = set ? use1 : use0;
                     WSP(0)
-                    if (use >= 1u) ws_wait(BAR(&B.acc_empty[set]), (use - 1u) & 1u, __LINE__);
+                    if (use >= 1u) ws_wait<100u>(BAR(&B.acc_empty[set]), (use - 1u) & 1u, __LINE__);
                     WSP(2)
                     tc_fence_after();
                     uint64_t bd = bdesc0;
                     uint32_t accum = 0u;
                     for (int pr = 0; pr < g.npairs; ++pr) {
-                        ws_wait(b_slot_full + 8u * (uint32_t)slot, round, __LINE__);
+                        ws_wait<100u>(b_slot_full + 8u * (uint32_t)slot, round, __LINE__);
                         WSP(3)
                         tc_fence_after();
                         if (mine) {
@@ -417,7 +425,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         for (;;) {
             const unsigned ws = P % WS_NWIN;
             WSP(0)
-            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
+            ws_wait<100u>(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
             WSP(1)
             const WsPoint &e = ent[P & (WS_NENT - 1)];
             if (e.done) break;
@@ -430,6 +438,13 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 WsTplRec &tr = trec[J & (WS_NENT - 1)];
                 // which angles can skip the bounds checks (warp-uniform)
                 unsigned inside_mask = 0;
+                // every sample lies within 0.7072 s + 2 px of (r1, c1) whatever the angle (the rotation keeps the template centre
+                // within 1 px of it): a point that far from the image border needs no per-angle test
+                {
+                    const double rad = 0.7072 * (double)s + 3.0;
+                    if (r1 >= rad && c1 >= rad && r1 <= (double)(a.rows1 - 1) - rad && c1 <= (double)(a.cols1 - 1) - rad) inside_mask = (1u << nb) - 1u;
+                }
+                if (inside_mask == 0u)
                 for (int ai = 0; ai < nb; ++ai) {
                     const double *tab = a.tab + 4 * (a0 + ai);
                     if (template_inside_warp(a.rows1, a.cols1, __dsub_rn(r1, tab[2]), __dsub_rn(c1, tab[3]), tab[0], tab[1], s))
@@ -613,14 +628,14 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         for (;;) {
             const unsigned ws = P % WS_NWIN;
             WSP(0)
-            ws_wait(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
+            ws_wait<100u>(BAR(&B.win_full[ws]), (P / WS_NWIN) & 1u, __LINE__);
             WSP(1)
             const WsPoint &e = ent[P & (WS_NENT - 1)];
             if (e.done) break;
             const int W = e.W, H = e.H, xoff = e.x0 & 15;
             const int RH = H - s + 1, RW = W - s + 1;
             const unsigned set = P % WS_NSTAT;
-            if (P >= WS_NSTAT) ws_wait(BAR(&B.stats_empty[set]), ((P / WS_NSTAT) - 1u) & 1u, __LINE__);
+            if (P >= WS_NSTAT) ws_wait<200u>(BAR(&B.stats_empty[set]), ((P / WS_NSTAT) - 1u) & 1u, __LINE__);
             WSP(2)
             double *wden = reinterpret_cast<double *>(ws_smem + g.off_stat + (size_t)set * g.stat_bytes);
             uint32_t *wsum = reinterpret_cast<uint32_t *>(wden + a.max_rr);
@@ -754,7 +769,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             for (int b = 0; b < nbatch; ++b) {
                 const unsigned J = P * (unsigned)nbatch + (unsigned)b;
                 WSP(0)
-                ws_wait(BAR(&B.acc_full[eg]), acc_use & 1u, __LINE__); ++acc_use;
+                ws_wait<100u>(BAR(&B.acc_full[eg]), acc_use & 1u, __LINE__); ++acc_use;
                 WSP(1)
                 if (b == 0 && all_done_s && n == total_pts_s[eg]) { leave = true; break; }
                 tc_fence_after();
@@ -763,7 +778,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 if (b == 0) {
                     pt = tr.pt; pi = tr.pi; W = tr.W; H = tr.H; xoff = tr.x0 & 15;
                     RH = H - s + 1; RW = W - s + 1; RR = RH * RW;
-                    ws_wait(BAR(&B.stats_full[sset]), (P / WS_NSTAT) & 1u, __LINE__);
+                    ws_wait<100u>(BAR(&B.stats_full[sset]), (P / WS_NSTAT) & 1u, __LINE__);
                 }
                 WSP(2)
                 const int a0 = b * per, nb = min(per, A_ - a0);
@@ -820,6 +835,8 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                         const double var = (double)tr.tsq[kk] * a.inv_area - mean[k] * mean[k];
                         lim2[k] = (float)(0.98 * var * (double)Nll);
                     }
+                    if (A_ == 1) m[0] = INFINITY;                                  // a single angle: nothing to screen
+                    else
                     for (int base = 0; base < RR; base += 256) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
