@@ -26,7 +26,7 @@ using namespace sid;
 
 namespace {
 #ifndef SID_WS_DEFAULT
-#define SID_WS_DEFAULT 0
+#define SID_WS_DEFAULT 1
 #endif
 
 constexpr size_t IMG_TAIL_SLACK = 4096;   // bytes readable past the last image row
@@ -475,7 +475,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
 
 extern "C" {
 
-const char *sid_version(void) { return "sea_ice_drift_b200 0.2 (sm_100a, exact-integer u8 tensor-core MCC)"; }
+const char *sid_version(void) { return "sea_ice_drift_b200 0.3 (sm_100a, exact-integer u8 tcgen05 MCC, warp-specialised pipeline)"; }
 
 int sid_create(sid_ctx **out, int device) {
     if (!out) return SID_EINVAL;

@@ -455,6 +455,52 @@ def test_tcgen05_path_equals_legacy_paths_bit_for_bit(gpu_ctx):
         assert np.array_equal(tables["tc"], tables["dp4a"], equal_nan=True), (s, len(angles))
 
 
+def test_warp_specialised_path_equals_legacy_paths_bit_for_bit(gpu_ctx):
+    """The warp-specialised pipeline kernel (pm_ws_kernel, the default for search radii <= 24) against the mma.sync and
+    tcgen05 row-loop kernels: every column of every row bit for bit, NaN rows and status included -- 1, 2, 3, 7 and 21
+    angles (the screening of the angles must pick the reference's winner), even / odd / wide templates, mixed borders,
+    a masked block (zero pixels -> NaN rows), bilinear sampling, raw Hessian and mcc_norm."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=36, side=1500, grid=24)
+    img1 = img1.copy()
+    img1[640:760, 700:820] = 0
+    rng = np.random.default_rng(4)
+    gpu_ctx.set_pair(img1, img2)
+    cases = ((35, [-3, 0, 3], 20, 20, {}), (35, [0], 8, 24, {}), (35, [-3, 3], 20, 22, dict(hes_norm=False, mcc_norm=True)),
+             (35, list(range(-10, 11)), 18, 24, {}), (35, [-9, -6, -3, 0, 3, 6, 9], 10, 24, {}), (50, [-3, 0, 3], 10, 20, {}),
+             (34, [-2, 2], 23, 23, dict(mcc_norm=True)), (21, [-3, 0, 3], 8, 14, {}), (64, [0, 5], 12, 20, {}), (9, [0], 3, 6, {}),
+             (35, [-3, 0, 3], 20, 24, dict(rot_order=1, hes_smth=True)), (35, [2, 2, 2], 20, 20, {}))
+    for s, angles, lo, hi, kw in cases:
+        brd = np.floor(rng.uniform(lo, hi + 1, len(c1)))
+        flags = _lib.flags_from_kwargs(kw.get("hes_norm", True), kw.get("hes_smth", False), kw.get("mcc_norm", False))
+        tables = {}
+        for path in ("ws", "imma", "tc"):
+            os.environ["SID_PM_PATH"] = path
+            try:
+                tables[path] = gpu_ctx.run(c1, r1, c2, r2, brd, s, angles, 0.5, kw.get("rot_order", 0), flags, want_status=True)
+            finally:
+                del os.environ["SID_PM_PATH"]
+        for other in ("imma", "tc"):
+            assert np.array_equal(tables["ws"][0], tables[other][0], equal_nan=True), (s, len(angles), other)
+            assert np.array_equal(tables["ws"][1], tables[other][1]), (s, len(angles), other)
+        assert np.isnan(tables["ws"][0][:, 0]).any() and np.isfinite(tables["ws"][0][:, 0]).sum() > 400
+
+
+def test_warp_specialised_kernel_is_the_default_for_small_search_radii(gpu_ctx):
+    """Default dispatch: pm_ws_kernel where its geometry fits (radius <= 24), the tcgen05 row-loop kernel or the mma.sync
+    kernel otherwise -- all with the same table."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=37, side=1200, grid=16)
+    gpu_ctx.set_pair(img1, img2)
+    for border in (20.0, 40.0):
+        brd = np.full(len(c1), border)
+        default = gpu_ctx.run(c1, r1, c2, r2, brd, 35, [-3, 0, 3], 0.5)
+        os.environ["SID_PM_PATH"] = "imma"
+        try:
+            legacy = gpu_ctx.run(c1, r1, c2, r2, brd, 35, [-3, 0, 3], 0.5)
+        finally:
+            del os.environ["SID_PM_PATH"]
+        assert np.array_equal(default, legacy, equal_nan=True), border
+
+
 def test_device_epilogue_equals_host_post_processing():
     """remainder add, pixel -> x/y / lon/lat, u/v differences and the _fill_gpi scatter on the device
     (sid_pm_epilogue_affine, table kept on the device) give the same seven grids, bit for bit, as the host lines that
