@@ -158,7 +158,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // uint8 2-D tensor map over image 2 with a box of box_w x box_h bytes (TMA window staging).
-bool make_window_tensor_map(sid_ctx *ctx, CUtensorMap *map, int box_w, int box_h) {
+bool make_window_tensor_map(sid_ctx *ctx, CUtensorMap *map, int box_w, int box_h, int which = 2) {
     if (!ctx->encode_tried) {
         ctx->encode_tried = true;
         cudaDriverEntryPointQueryResult q;
@@ -169,12 +169,13 @@ bool make_window_tensor_map(sid_ctx *ctx, CUtensorMap *map, int box_w, int box_h
         else
             cudaGetLastError();
     }
-    if (!ctx->encode_tiled || box_w > 256 || box_h > 256 || (box_w & 15) || (ctx->pitch2 & 15)) return false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)ctx->cols2, (cuuint64_t)ctx->rows2};
-    const cuuint64_t gstride[1] = {(cuuint64_t)ctx->pitch2};
+    const long long pitch = which == 1 ? ctx->pitch1 : ctx->pitch2;
+    if (!ctx->encode_tiled || box_w > 256 || box_h > 256 || (box_w & 15) || (pitch & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(which == 1 ? ctx->cols1 : ctx->cols2), (cuuint64_t)(which == 1 ? ctx->rows1 : ctx->rows2)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->img2.p, gdim, gstride, box,
+    const CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, which == 1 ? ctx->img1.p : ctx->img2.p, gdim, gstride, box,
                                                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -226,9 +227,12 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     // warp-specialised pipeline kernel (sid_pm_ws_kernel.cuh): small result maps (radius <= 24), needs the split tail
     PmWsCfg wg;
     memset(&wg, 0, sizeof wg);
+    alignas(64) CUtensorMap tmap1;                  // image 1: the patch the templates of a point are sampled from
+    memset(&tmap1, 0, sizeof tmap1);
     bool use_ws = false;
     if (want_ws && split_tail && pm_ws_geometry(s, Rmax, Wmax, n_angles, a.max_rr, wg) &&
-        (size_t)wg.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows))
+        (size_t)wg.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows) &&
+        make_window_tensor_map(ctx, &tmap1, wg.pbw, wg.pbh, 1))
         use_ws = true;
     if (use_ws) {
         a.tma = 1; a.ab = wg.nab;
@@ -255,7 +259,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         CU(cudaMemsetAsync(ctx->scratch.p, 0, (size_t)grid * 6 * 8 * 8, st));
         a.scratch = (unsigned char *)ctx->scratch.p;
 #endif
-        void *params_ws[] = {(void *)&a, (void *)&wg, (void *)&tmap};
+        void *params_ws[] = {(void *)&a, (void *)&wg, (void *)&tmap, (void *)&tmap1};
         if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
         CU(cudaEventRecord(ctx->k_ev[0], st));
         CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)WS_THREADS), params_ws, (size_t)wg.smem_bytes, st));

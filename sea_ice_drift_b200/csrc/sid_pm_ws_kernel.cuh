@@ -41,7 +41,7 @@ constexpr int WS_W_MMA = 1, WS_W_GATHER = 5, WS_W_STATS = 13, WS_W_EPI = 20;
 constexpr int WS_NST = 7 * 32;            // stats threads
 constexpr int WS_NSTAT = 3;               // sets of window statistics (stats warps run up to 3 points ahead of the epilogue)
 constexpr int WS_NG = 8;                  // gather warps
-constexpr int WS_NWIN = 3;                // window ring
+constexpr int WS_NWIN = 2;                // window ring (each slot: the search window of image 2 + the template patch of image 1)
 constexpr int WS_NENT = 8;                // point entries / template records
 constexpr int WS_MAX_SLOTS = 8;
 constexpr int WS_ACC_COLS = 256;          // tensor-memory columns per accumulator set (4 x blocks x 64)
@@ -78,6 +78,9 @@ struct PmWsCfg {
     int cpl;          // words per angle plane of the combined correlation buffer
     int hs_words;     // words per transposed horizontal-sum array
     unsigned inv_nw1; // ceil(2^32 / (nwords + 1))
+    int pbw, pbh;     // template patch of image 1 (TMA box, bytes x rows): every sample of every angle lies inside
+    int prad;         // its half size: ceil(0.7072 s + 3)
+    int patch_bytes;
     int off_a, off_tpl, tpl_buf_words, off_stat, stat_bytes, off_hs, off_c, smem_bytes;
 };
 
@@ -99,7 +102,12 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     if (g.npanels < g.np_load) g.npanels = g.np_load;
     g.load_rows = Wmax;
     g.wrows = (Wmax + 7) & ~7;
-    g.win_bytes = g.npanels * g.wrows * 16;
+    g.prad = (int)(0.7072 * (double)s + 3.0) + 1;
+    g.pbw = (2 * g.prad + 2 + 15 + 15) & ~15;        // the box starts at a 16-byte aligned column
+    g.pbh = 2 * g.prad + 2;
+    if (g.pbw > 256 || g.pbh > 256) return false;
+    g.patch_bytes = (g.pbw * g.pbh + 127) & ~127;
+    g.win_bytes = g.npanels * g.wrows * 16 + g.patch_bytes;
     g.hp = Wmax | 1;
     g.cpl = (max_rr + 31) & ~31;
     g.inv_nw1 = (unsigned)((0x100000000ull + (unsigned)g.nwords) / (unsigned)(g.nwords + 1));
@@ -122,7 +130,7 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     return true;
 }
 
-struct WsPoint { double c1, r1; long long pt, pi; int x0, y0, W, H; int done, pad; };
+struct WsPoint { double c1, r1; long long pt, pi; int x0, y0, W, H; int done, px0, py0, pad; };
 struct WsTplRec { long long pt, pi; int x0, W, H, zero; uint32_t tsum[3], tsq[3]; };
 struct WsBars {
     unsigned long long win_full[WS_NWIN], win_empty[WS_NWIN];
@@ -229,7 +237,7 @@ __device__ __forceinline__ unsigned long long ws_exact_pass(const int32_t *__res
 }
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
-pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMap tmapP) {
+pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmap1) {
     extern __shared__ __align__(128) unsigned char ws_smem[];
     __shared__ WsBars B;
     __shared__ WsPoint ent[WS_NENT];
@@ -277,7 +285,8 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
     if (warp == 0) {
         // ================================================================ control
         if (lane == 0) {
-            const unsigned win_tx = (unsigned)(g.np_load * g.load_rows * 16);
+            const unsigned win_tx = (unsigned)(g.np_load * g.load_rows * 16 + g.pbw * g.pbh);
+            const int patch_off = g.npanels * g.wrows * 16;
             unsigned P = 0;
             WSP_DECL
             unsigned pi = atomicAdd(a.counter, 1u);
@@ -305,10 +314,15 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     WsPoint &e = ent[P & (WS_NENT - 1)];
                     e.c1 = c1; e.r1 = r1; e.pt = pt; e.pi = (long long)pi;
                     e.x0 = (int)x0; e.y0 = (int)y0; e.W = W; e.H = H; e.done = 0;
+                    const int pxa = ((int)floor(c1) - g.prad) & ~15, py = (int)floor(r1) - g.prad;
+                    e.px0 = pxa; e.py0 = py;
                     mbar_expect_tx(&B.win_full[ws], win_tx);
                     const int xa = (int)x0 - (int)(x0 & 15);
                     for (int p = 0; p < g.np_load; ++p)
                         tma_load_2d(sWin + (size_t)ws * g.win_bytes + (size_t)p * PS, &tmapP, xa + 16 * p, (int)y0, &B.win_full[ws]);
+                    // template patch of image 1 around (c1, r1); out-of-image bytes read 0 (the gather only uses it for points
+                    // whose samples all lie inside the image)
+                    tma_load_2d(sWin + (size_t)ws * g.win_bytes + patch_off, &tmap1, pxa, py, &B.win_full[ws]);
                     ++P;
                 }
                 pi = pi_next;
@@ -432,6 +446,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             const double c1 = e.c1, r1 = e.r1;
             const long long e_pt = e.pt, e_pi = e.pi;
             const int e_x0 = e.x0, e_W = e.W, e_H = e.H;
+            const uint8_t *patch = sWin + (size_t)ws * g.win_bytes + (size_t)g.npanels * PS - ((size_t)e.py0 * g.pbw + e.px0);
             for (int a0 = 0; a0 < A_; a0 += per, ++J) {
                 const int nb = min(per, A_ - a0);
                 uint32_t *buf = sTpl + (J & 1u) * g.tpl_buf_words;
@@ -484,7 +499,9 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                                 for (int k = 0; k < 4; ++k) {
                                     const double row = __dadd_rn(br, __dmul_rn(djv[k], sn));
                                     const double col = __dadd_rn(bc, __dmul_rn(djv[k], cs));
-                                    v[u][k] = template_sample<false>(a.img1, a.rows1, a.cols1, a.pitch1, row, col, 0);
+                                    // nearest sample (scipy order 0: floor(x + 0.5)) out of the staged patch of image 1
+                                    const int ri = __double2int_rd(__dadd_rn(row, 0.5)), ci = __double2int_rd(__dadd_rn(col, 0.5));
+                                    v[u][k] = patch[ri * g.pbw + ci];
                                 }
                             }
 #pragma unroll
