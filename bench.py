@@ -318,6 +318,7 @@ def main_ours(args):
         step_resident()
         k_samples.append(ctx.last_kernel_ms)
     kernel_ms = float(np.mean(k_samples))
+    kernel_name = ctx.last_kernel_name
 
     # ---- end to end through the C ABI with host buffers ("e2e")
     ctx.set_stream(None)
@@ -452,8 +453,9 @@ def main_ours(args):
         # bounding roofline is "tensor" against the measured dense bf16 peak of MEASURED_PEAKS.json
         roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                     "frac": achieved / tensor_peak, "traffic": traffic,
-                    "kernel": "sid::pm_tc_kernel", "kernel_ms": kernel_ms, "step_ms": ms_per_step,
-                    "kernels_per_step": "pm_tc_kernel (tcgen05 correlation, dominant) + pm_tail_kernel (peak statistics)",
+                    "kernel": kernel_name, "kernel_ms": kernel_ms, "step_ms": ms_per_step,
+                    "kernels_per_step": "%s (correlation on tcgen05.mma kind::i8, dominant) + pm_tail_kernel (peak statistics)"
+                                        % kernel_name.split("::")[-1],
                     "algorithmic_flops_per_launch": flops_step,
                     "peak_source": ("bf16_tflops of MEASURED_PEAKS.json (of measured)" if peaks.get("bf16_tflops")
                                     else "1.59 PFLOP/s (of fallback)"),
@@ -462,10 +464,12 @@ def main_ours(args):
                     "frac_of_fp32_fma_peak": achieved / peak_tflops,
                     "note": "algorithmic FLOPs = sum over points and angles of 2 s^2 R^2 (SURVEY 8d), multiply-adds of the direct-form "
                             "correlation only; they run as tcgen05.mma kind::i8 (u8 x u8 -> s32, TMEM accumulators; measured pipe rate "
-                            "7949 MAC/clk/SM = u8_tcgen05_peak, profiles/r02_tcgen05_i8_rates.txt). The Toeplitz formulation issues "
-                            "~3.3x the algorithmic MACs and the tensor pipe is ~10 % busy: the kernel is bound by the latency chains of "
-                            "its non-MAC phases (template gather, FP64 normalisation, window statistics) at 16 resident warps per SM "
-                            "(profiles/README.md). BASELINE.json's own figure, the fraction of the FP32-FMA roofline, is in roofline_fma",
+                            "7949 MAC/clk/SM = u8_tcgen05_peak, profiles/r02_tcgen05_i8_rates.txt). pm_ws_kernel (default for search "
+                            "radii <= 24) is a warp-specialised pipeline, one CTA of 28 warps per SM: the tensor pipe is ~15 % busy and no "
+                            "pipe is saturated; the time is set by the instruction latency chains of the gather / window-statistics / "
+                            "normalisation roles at 28 resident warps (ncu: 13 cycles per issued warp instruction, IPC 2.1; "
+                            "profiles/r02_pm_ws_ncu_roles.txt). BASELINE.json's own figure, the fraction of the FP32-FMA roofline, is in "
+                            "roofline_fma",
                     "hbm_gbs_measured_peak": peaks.get("hbm_gbs")}
         roofline_fma = {"bound": "fma", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                         "frac": achieved / peak_tflops, "traffic": traffic,

@@ -171,6 +171,10 @@ int64_t sid_launch_count(const sid_ctx *ctx);
 /* Device time (ms, CUDA events on the launching stream) of the most recent launch of the fused
  * point kernel; waits for it to finish.  -1 if nothing was launched yet. */
 double sid_last_kernel_ms(sid_ctx *ctx);
+/* Name of the point kernel the most recent launch used ("sid::pm_ws_kernel", "sid::pm_tc_kernel",
+ * "sid::pm_points_kernel<imma>", "sid::pm_points_kernel<dp4a>"); "" before the first launch.  The paths
+ * are interchangeable (bit-identical tables); the dispatch picks by search radius. */
+const char *sid_last_kernel_name(const sid_ctx *ctx);
 
 /* rotate_and_match for one point against an explicit search window `image2`
  * (host pointers).  Outputs: *valid (0 -> the reference returns 7 x NaN),

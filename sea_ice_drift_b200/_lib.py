@@ -22,7 +22,7 @@ SID_HES_NORM, SID_HES_SMTH, SID_MCC_NORM = 1, 2, 4
 
 EXPORTS = [
     "sid_version", "sid_create", "sid_destroy", "sid_last_error", "sid_set_stream", "sid_synchronize",
-    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_upload_rows", "sid_pm_epilogue_affine", "sid_first_guess", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms",
+    "sid_set_pair", "sid_set_pair_device", "sid_pair_layout", "sid_adopt_pair_device", "sid_upload_rows", "sid_pm_epilogue_affine", "sid_first_guess", "sid_run", "sid_run_pair", "sid_run_device", "sid_launch_count", "sid_last_kernel_ms", "sid_last_kernel_name",
     "sid_rotate_and_match", "sid_get_template", "sid_match_template", "sid_get_hessian", "sid_knn_hamming2",
     "sid_deformation",
 ]
@@ -59,6 +59,8 @@ def load_library():
         lib.sid_launch_count.restype = C.c_int64
         lib.sid_last_kernel_ms.argtypes = [C.c_void_p]
         lib.sid_last_kernel_ms.restype = C.c_double
+        lib.sid_last_kernel_name.argtypes = [C.c_void_p]
+        lib.sid_last_kernel_name.restype = C.c_char_p
         pair = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int64]
         lib.sid_set_pair.argtypes = pair
         lib.sid_set_pair_device.argtypes = pair
@@ -170,6 +172,10 @@ class Context(object):
     @property
     def last_kernel_ms(self):
         return float(self._lib.sid_last_kernel_ms(self._h))
+
+    @property
+    def last_kernel_name(self):
+        return self._lib.sid_last_kernel_name(self._h).decode()
 
     def set_stream(self, cuda_stream):
         """None -> the context's own stream; 0 -> CUDA's legacy default stream (what

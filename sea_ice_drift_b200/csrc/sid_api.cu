@@ -62,6 +62,7 @@ struct sid_ctx {
     size_t pin_cap = 0;
     cudaEvent_t k_ev[2] = {};                // bracket the last fused-kernel launch (sid_last_kernel_ms)
     bool k_ev_valid = false;
+    const char *k_name = "";
     long long table_n = -1;                  // rows of the result table the last sid_run / sid_run_pair left in `out`
     long long tail_hint_n = 0;               // total points of the current host call (sizes the tail hand-off once)
     // staged upload of pageable host images (sid_run_pair): pinned double buffer + "slot free again" events
@@ -265,6 +266,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)WS_THREADS), params_ws, (size_t)wg.smem_bytes, st));
         CU(cudaEventRecord(ctx->k_ev[1], st));
         ctx->k_ev_valid = true;
+        ctx->k_name = "sid::pm_ws_kernel";
         ctx->launches += 1;
 #ifdef SID_WS_PROF
         {
@@ -464,6 +466,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, st));
     CU(cudaEventRecord(ctx->k_ev[1], st));
     ctx->k_ev_valid = true;
+    ctx->k_name = use_tc ? "sid::pm_tc_kernel" : imma ? "sid::pm_points_kernel<imma>" : "sid::pm_points_kernel<dp4a>";
     ctx->launches += 1;
     if (split_tail) {
         const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
@@ -540,6 +543,8 @@ int sid_synchronize(sid_ctx *ctx) {
 }
 
 int64_t sid_launch_count(const sid_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+const char *sid_last_kernel_name(const sid_ctx *ctx) { return ctx ? ctx->k_name : ""; }
 
 double sid_last_kernel_ms(sid_ctx *ctx) {
     if (!ctx || !ctx->k_ev_valid) return -1.0;
