@@ -6,11 +6,12 @@ img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=1, side=700, g
 b = np.floor(np.random.default_rng(0).uniform(20, 30, b.size))
 ctx = _lib.Context(0)
 out = ctx.run_pair(img1, img2, c1, r1, c2, r2, b, 35, [-3, 0, 3], 0.0)
-# search radius <= 24: the warp-specialised pipeline kernel (pm_ws_kernel), 3 and 7 angles, mixed borders, single angle
-b20 = np.floor(np.random.default_rng(3).uniform(8, 25, b.size))
+# search radius <= 20 (s = 35; the shared-memory budget decides): the warp-specialised pipeline kernel (pm_ws_kernel), 3 and 7 angles, mixed borders, single angle
+b20 = np.floor(np.random.default_rng(3).uniform(8, 21, b.size))
 out_ws = ctx.run(c1, r1, c2, r2, b20, 35, [-3, 0, 3], 0.0); name_ws = ctx.last_kernel_name
 out_ws7 = ctx.run(c1, r1, c2, r2, b20, 34, list(range(-3, 4)), 0.0, rot_order=1, flags=7)
 out_ws1 = ctx.run(c1, r1, c2, r2, b20, 21, [0], 0.0)
+assert name_ws == "sid::pm_ws_kernel", name_ws
 print("ws", name_ws, np.isnan(out_ws[:, 0]).sum(), np.isnan(out_ws7[:, 0]).sum(), np.isnan(out_ws1[:, 0]).sum())
 out2 = ctx.run(c1, r1, c2, r2, b, 35, list(range(-3, 4)), 0.0, rot_order=1, flags=7)
 out3 = ctx.run(c1[:20], r1[:20], c2[:20], r2[:20], b[:20] + 40, 50, [0, 2], 0.0)

@@ -225,7 +225,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     PmTcCfg tg;
     memset(&tg, 0, sizeof tg);
     bool use_tc = false;
-    // warp-specialised pipeline kernel (sid_pm_ws_kernel.cuh): small result maps (radius <= 24), needs the split tail
+    // warp-specialised pipeline kernel (sid_pm_ws_kernel.cuh): small result maps (geometry: radius <= 24; its shared-memory layout fits 227 KB up to radius 20 at s = 35), needs the split tail
     PmWsCfg wg;
     memset(&wg, 0, sizeof wg);
     alignas(64) CUtensorMap tmap1;                  // image 1: the patch the templates of a point are sampled from
@@ -243,9 +243,10 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
         a.split_tail = 1;
         const size_t cap_n = (size_t)std::max<long long>(n + tail_off, ctx->tail_hint_n);
-        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.max_rr * sizeof(float)))) return rc;
+        a.tail_stride = (a.max_rr + 3) & ~3;
+        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.tail_stride * sizeof(float)))) return rc;
         if ((rc = reserve(ctx, ctx->tail_recs, cap_n * sizeof(PmTailRec)))) return rc;
-        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.max_rr;
+        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.tail_stride;
         a.tail_recs = (PmTailRec *)ctx->tail_recs.p + tail_off;
         const void *kfn = (const void *)pm_ws_kernel;
         if (int arc = allow_max_smem(ctx, kfn)) return arc;
@@ -453,9 +454,10 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     a.split_tail = split_tail ? 1 : 0;
     if (split_tail) {
         const size_t cap_n = (size_t)std::max<long long>(n + tail_off, ctx->tail_hint_n);
-        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.max_rr * sizeof(float)))) return rc;
+        a.tail_stride = (a.max_rr + 3) & ~3;
+        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.tail_stride * sizeof(float)))) return rc;
         if ((rc = reserve(ctx, ctx->tail_recs, cap_n * sizeof(PmTailRec)))) return rc;
-        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.max_rr;
+        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.tail_stride;
         a.tail_recs = (PmTailRec *)ctx->tail_recs.p + tail_off;
     }
     void *params_legacy[] = {(void *)&a, (void *)&tmap};
@@ -622,7 +624,7 @@ int sid_upload_rows(sid_ctx *ctx, uint8_t *d_dst, int64_t dst_pitch, const uint8
 }
 
 static int upload_angles(sid_ctx *ctx, int n_angles, const double *angles, const double *angle_tab,
-                         const double **d_angles, const double **d_tab) {
+                         const double **d_angles, const double **d_tab, cudaStream_t st = nullptr) {
     const size_t bytes = (size_t)n_angles * 5 * sizeof(double);
     int rc = reserve(ctx, ctx->angles, bytes);
     if (rc) return rc;
@@ -630,7 +632,7 @@ static int upload_angles(sid_ctx *ctx, int n_angles, const double *angles, const
     for (int k = 0; k < n_angles; ++k) h[k] = angles ? angles[k] : (double)k;
     memcpy(h.data() + n_angles, angle_tab, (size_t)n_angles * 4 * sizeof(double));
     // small pageable copy: the runtime stages it before returning, so `h` may go out of scope
-    CU(cudaMemcpyAsync(ctx->angles.p, h.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->angles.p, h.data(), bytes, cudaMemcpyHostToDevice, st ? st : ctx->stream));
     *d_angles = (const double *)ctx->angles.p;
     *d_tab = *d_angles + n_angles;
     return SID_OK;
@@ -694,71 +696,47 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
     }
     if (n == 0) return SID_OK;
 
-    // ---- bands (upload granularity); a single band means "everything is already resident"
+    // ---- bands (upload granularity); a single band means "everything is already resident".  The bands TAPER: while the
+    //      upload runs the kernels of band k hide behind the copy of band k + 1, but the kernels of the LAST band run after
+    //      the last byte has arrived -- so the last bands are short (weights below; SID_BAND_PLAN="w0,w1,..." overrides,
+    //      SID_BANDS=n gives n equal bands).  Boundaries are multiples of 64 rows.
     const int rows1 = pair ? pair->rows1 : ctx->rows1, rows2 = pair ? pair->rows2 : ctx->rows2;
     const int max_rows = std::max(rows1, rows2);
     int nbands = 1;
-    if (pair) nbands = std::max(1, std::min(8, max_rows / 512));     // 8 bands measured best (more = more launch tails)
-    if (pair) if (const char *e = getenv("SID_BANDS")) nbands = std::max(1, std::min(MAX_BANDS, atoi(e)));
-    const int band_rows = (max_rows + nbands - 1) / nbands;
-
-    // ---- borders: bound, typical value, and the processing order: band of the last image row a point
-    //      touches first, then largest window first (counting sort on the combined key)
-    int max_border = 0;
-    std::vector<int> ib((size_t)n), band((size_t)n, 0);
-    const double ext = 0.5 * std::sqrt(2.0) * (img_size + 2) + 3.0;      // template reach around (c1, r1) incl. rounding
-    const int hws = img_size / 2;
-    for (int64_t i = 0; i < n; ++i) {
-        const double b = border[i];
-        int v = 0;
-        if (std::isfinite(b) && b >= 0.0 && b < 4096.0) v = (int)std::ceil(b);   // fractional borders: the window can be one pixel wider
-        ib[(size_t)i] = v;
-        max_border = std::max(max_border, v);
-        if (nbands > 1) {
-            double need = 0.0;
-            if (std::isfinite(r1[i]) && std::isfinite(r2fg[i])) need = std::max(r1[i] + ext, r2fg[i] + hws + v + 2.0);
-            int k = need <= 0.0 ? 0 : (int)std::min((double)(nbands - 1), need / band_rows);
-            band[(size_t)i] = k;
+    std::vector<double> weights;
+    if (pair) {
+        if (max_rows >= 8192) weights = {6, 6, 6, 6, 6, 5, 4, 3, 2, 1};
+        else weights.assign((size_t)std::max(1, std::min(8, max_rows / 512)), 1.0);
+        if (const char *e = getenv("SID_BANDS")) weights.assign((size_t)std::max(1, std::min(MAX_BANDS, atoi(e))), 1.0);
+        if (const char *e = getenv("SID_BAND_PLAN")) {
+            std::vector<double> w;
+            for (const char *q = e; *q && (int)w.size() < MAX_BANDS;) {
+                char *end = nullptr;
+                const double v = strtod(q, &end);
+                if (end == q) break;
+                if (v > 0.0) w.push_back(v);
+                q = (*end == ',') ? end + 1 : end;
+            }
+            if (!w.empty()) weights = w;
         }
+        nbands = (int)weights.size();
     }
-    const size_t nkeys = (size_t)nbands * (size_t)(max_border + 1);
-    std::vector<int> hist(nkeys + 1, 0);
-    auto key_of = [&](int64_t i) { return (size_t)band[(size_t)i] * (size_t)(max_border + 1) + (size_t)(max_border - ib[(size_t)i]); };
-    for (int64_t i = 0; i < n; ++i) ++hist[key_of(i) + 1];
-    for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
-    std::vector<int> band_start((size_t)nbands + 1, 0);
-    for (int k = 0; k <= nbands; ++k) band_start[(size_t)k] = hist[std::min(nkeys, (size_t)k * (size_t)(max_border + 1))];
-    int typ_border = max_border;
-    {   // median border = typical point
-        std::vector<long long> per_b((size_t)max_border + 1, 0);
-        for (int64_t i = 0; i < n; ++i) ++per_b[(size_t)ib[(size_t)i]];
-        long long acc = 0;
-        for (int b = max_border; b >= 0; --b) { acc += per_b[(size_t)b]; if (acc > n / 2) { typ_border = b; break; } }
+    std::vector<int> band_lo((size_t)nbands + 1, 0);
+    {
+        double total = 0.0, acc = 0.0;
+        for (double w : weights) total += w;
+        for (int k = 1; k < nbands; ++k) {
+            acc += weights[(size_t)k - 1];
+            int y = (int)((double)max_rows * acc / total / 64.0 + 0.5) * 64;
+            band_lo[(size_t)k] = std::max(band_lo[(size_t)k - 1], std::min(max_rows, y));
+        }
+        band_lo[(size_t)nbands] = max_rows;
     }
-
-    const size_t pts_bytes = (size_t)n * 5 * sizeof(double);
-    const size_t ord_bytes = (size_t)n * sizeof(int);
-    const size_t out_bytes = (size_t)n * 5 * sizeof(double);
-    const size_t st_bytes = (size_t)n * sizeof(int);
-    rc = reserve_pinned(ctx, pts_bytes + ord_bytes + out_bytes + st_bytes + 64);
-    if (rc) return rc;
-    if ((rc = reserve(ctx, ctx->pts, pts_bytes))) return rc;
-    if ((rc = reserve(ctx, ctx->order, ord_bytes))) return rc;
-    if ((rc = reserve(ctx, ctx->out, out_bytes))) return rc;
-    if ((rc = reserve(ctx, ctx->status, st_bytes))) return rc;
-
-    double *hp = (double *)ctx->pin;
-    memcpy(hp, c1, (size_t)n * 8); memcpy(hp + n, r1, (size_t)n * 8); memcpy(hp + 2 * n, c2fg, (size_t)n * 8);
-    memcpy(hp + 3 * n, r2fg, (size_t)n * 8); memcpy(hp + 4 * n, border, (size_t)n * 8);
-    int *hord = (int *)((char *)ctx->pin + pts_bytes);
-    for (int64_t i = 0; i < n; ++i) hord[hist[key_of(i)]++] = (int)i;
-
-    // ---- small uploads FIRST: host-to-device copies of all streams share the copy engine in issue order,
-    //      so anything enqueued behind the image bands would hold the first kernel back until they are done
-    CU(cudaMemcpyAsync(ctx->pts.p, hp, pts_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->order.p, hord, ord_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    const double *d_angles, *d_tab;
-    if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab))) return rc;
+    int band_rows = 0;                                          // tallest band (sizes the staging slots)
+    for (int k = 0; k < nbands; ++k) band_rows = std::max(band_rows, band_lo[(size_t)k + 1] - band_lo[(size_t)k]);
+    std::vector<unsigned char> band_of64((size_t)max_rows / 64 + 2, (unsigned char)(nbands - 1));
+    for (int k = 0, j = 0; k < nbands; ++k)
+        for (; j * 64 < band_lo[(size_t)k + 1] && (size_t)j < band_of64.size(); ++j) band_of64[(size_t)j] = (unsigned char)k;
 
     // ---- image upload in bands on the copy stream
     if (pair) {
@@ -801,8 +779,8 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
         for (int k = 0; k < 2; ++k) if (!ctx->stage_event[k]) CU(cudaEventCreateWithFlags(&ctx->stage_event[k], cudaEventDisableTiming));
     }
     auto enqueue_band_copy = [&](int k) -> int {
-        const int ya = k * band_rows;
-        const int n1 = std::min(band_rows, pair->rows1 - ya), n2 = std::min(band_rows, pair->rows2 - ya);
+        const int ya = band_lo[(size_t)k], nrows = band_lo[(size_t)k + 1] - ya;
+        const int n1 = std::min(nrows, pair->rows1 - ya), n2 = std::min(nrows, pair->rows2 - ya);
         const uint8_t *s1 = pair->img1 + (size_t)ya * pair->pitch1, *s2 = pair->img2 + (size_t)ya * pair->pitch2;
         size_t sp1 = (size_t)pair->pitch1, sp2 = (size_t)pair->pitch2;
         if (staged) {
@@ -823,19 +801,85 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
         CU(cudaEventRecord(ctx->band_event[k], ctx->copy_stream));
         return SID_OK;
     };
+    // band 0 goes out before the host-side preparation below (point order, small uploads), which then overlaps its DMA;
+    // the small uploads queue behind it on the copy engine (the first kernel needs band 0 anyway), the other bands behind them
+    if (pair && !staged && (rc = enqueue_band_copy(0))) return rc;
+
+    // ---- borders: bound, typical value, and the processing order: band of the last image row a point
+    //      touches first, then largest window first (counting sort on the combined key)
+    int max_border = 0;
+    std::vector<int> ib((size_t)n), band((size_t)n, 0);
+    const double ext = 0.5 * std::sqrt(2.0) * (img_size + 2) + 3.0;      // template reach around (c1, r1) incl. rounding
+    const int hws = img_size / 2;
+    for (int64_t i = 0; i < n; ++i) {
+        const double b = border[i];
+        int v = 0;
+        if (std::isfinite(b) && b >= 0.0 && b < 4096.0) v = (int)std::ceil(b);   // fractional borders: the window can be one pixel wider
+        ib[(size_t)i] = v;
+        max_border = std::max(max_border, v);
+        if (nbands > 1) {
+            double need = 0.0;
+            if (std::isfinite(r1[i]) && std::isfinite(r2fg[i])) need = std::max(r1[i] + ext, r2fg[i] + hws + v + 2.0);
+            band[(size_t)i] = need <= 0.0 ? 0 : (int)band_of64[(size_t)std::min((double)(band_of64.size() - 1), need / 64.0)];
+        }
+    }
+    const size_t nkeys = (size_t)nbands * (size_t)(max_border + 1);
+    std::vector<int> hist(nkeys + 1, 0);
+    auto key_of = [&](int64_t i) { return (size_t)band[(size_t)i] * (size_t)(max_border + 1) + (size_t)(max_border - ib[(size_t)i]); };
+    for (int64_t i = 0; i < n; ++i) ++hist[key_of(i) + 1];
+    for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
+    std::vector<int> band_start((size_t)nbands + 1, 0);
+    for (int k = 0; k <= nbands; ++k) band_start[(size_t)k] = hist[std::min(nkeys, (size_t)k * (size_t)(max_border + 1))];
+    int typ_border = max_border;
+    {   // median border = typical point
+        std::vector<long long> per_b((size_t)max_border + 1, 0);
+        for (int64_t i = 0; i < n; ++i) ++per_b[(size_t)ib[(size_t)i]];
+        long long acc = 0;
+        for (int b = max_border; b >= 0; --b) { acc += per_b[(size_t)b]; if (acc > n / 2) { typ_border = b; break; } }
+    }
+
+    const size_t pts_bytes = (size_t)n * 5 * sizeof(double);
+    const size_t ord_bytes = (size_t)n * sizeof(int);
+    const size_t out_bytes = (size_t)n * 5 * sizeof(double);
+    const size_t st_bytes = (size_t)n * sizeof(int);
+    rc = reserve_pinned(ctx, pts_bytes + ord_bytes + out_bytes + st_bytes + 64);
+    if (rc) return rc;
+    if ((rc = reserve(ctx, ctx->pts, pts_bytes))) return rc;
+    if ((rc = reserve(ctx, ctx->order, ord_bytes))) return rc;
+    if ((rc = reserve(ctx, ctx->out, out_bytes))) return rc;
+    if ((rc = reserve(ctx, ctx->status, st_bytes))) return rc;
+
+    double *hp = (double *)ctx->pin;
+    memcpy(hp, c1, (size_t)n * 8); memcpy(hp + n, r1, (size_t)n * 8); memcpy(hp + 2 * n, c2fg, (size_t)n * 8);
+    memcpy(hp + 3 * n, r2fg, (size_t)n * 8); memcpy(hp + 4 * n, border, (size_t)n * 8);
+    int *hord = (int *)((char *)ctx->pin + pts_bytes);
+    for (int64_t i = 0; i < n; ++i) hord[hist[key_of(i)]++] = (int)i;
+
+    // ---- small uploads.  With pinned images they go on the COPY stream, between band 0 and band 1: the copy engine serves
+    //      one stream's queue in order, but between streams it does not keep the issue order (measured: point arrays enqueued
+    //      on the compute stream while band 0 was in flight were served after ALL bands -- 8.3 instead of 5.0 ms per pair).
+    //      The staged path enqueues its bands one by one below, so there the small uploads simply go first.
+    cudaStream_t up = (pair && !staged) ? ctx->copy_stream : ctx->stream;
+    CU(cudaMemcpyAsync(ctx->pts.p, hp, pts_bytes, cudaMemcpyHostToDevice, up));
+    CU(cudaMemcpyAsync(ctx->order.p, hord, ord_bytes, cudaMemcpyHostToDevice, up));
+    const double *d_angles, *d_tab;
+    if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab, up))) return rc;
+    if (!ctx->slot_event[0])
+        for (int k = 0; k < 3; ++k) CU(cudaEventCreateWithFlags(&ctx->slot_event[k], cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->slot_event[0], up));                       // point / angle uploads are enqueued
+
     if (pair && !staged)
-        for (int k = 0; k < nbands; ++k) if ((rc = enqueue_band_copy(k))) return rc;
+        for (int k = 1; k < nbands; ++k) if ((rc = enqueue_band_copy(k))) return rc;
 
     const double *dp = (const double *)ctx->pts.p;
     ctx->tail_hint_n = n;
     const bool two_streams = pair && nbands > 1;
     if (two_streams) {
-        if (!ctx->band_stream[0]) {
+        if (!ctx->band_stream[0])
             for (int k = 0; k < 2; ++k) CU(cudaStreamCreateWithFlags(&ctx->band_stream[k], cudaStreamNonBlocking));
-            for (int k = 0; k < 3; ++k) CU(cudaEventCreateWithFlags(&ctx->slot_event[k], cudaEventDisableTiming));
-        }
-        CU(cudaEventRecord(ctx->slot_event[0], ctx->stream));            // point / angle uploads are enqueued
         for (int k = 0; k < 2; ++k) CU(cudaStreamWaitEvent(ctx->band_stream[k], ctx->slot_event[0], 0));
+    } else if (up != ctx->stream) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->slot_event[0], 0));
     }
     for (int k = 0; k < nbands; ++k) {
         if (staged && (rc = enqueue_band_copy(k))) return rc;

@@ -782,7 +782,7 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
         const int best_slot = S.best_slot, best_idx = S.best_idx;
         const float *best = maps + (size_t)best_slot * a.max_rr;
         if (a.split_tail) {
-            float *dst = a.tail_maps + (size_t)pi * a.max_rr;
+            float *dst = a.tail_maps + (size_t)pi * a.tail_stride;
             for (int k = tid; k < RR; k += nt) dst[k] = best[k];
             if (tid == 0) {
                 PmTailRec rec;

@@ -883,7 +883,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 WSP(5)
                 ws_bar(barid, 128);
                 WSP(4)
-                float M[3], Mx = -INFINITY;
+                float M[3], Mx = -INFINITY;                               // ---- contenders (within the margin of the best estimate) -> exact normalisation, argmax, hand-off
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const float sc = (k < nb && !E.st[k].flat) ? (float)(1.0 / E.st[k].norm) : 0.0f;
@@ -897,7 +897,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 int ncont = 0, first = -1;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) if (k < nb && M[k] >= thr) { ++ncont; if (first < 0) first = k; }
-                float *dst = a.tail_maps + (size_t)pi * a.max_rr;
+                float *dst = a.tail_maps + (size_t)pi * a.tail_stride;
                 // group-wide maximum of a key (all threads return the same value)
                 auto group_max = [&](unsigned long long key) -> unsigned long long {
                     key = warp_max_u64(key);
