@@ -231,7 +231,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     alignas(64) CUtensorMap tmap1;                  // image 1: the patch the templates of a point are sampled from
     memset(&tmap1, 0, sizeof tmap1);
     bool use_ws = false;
-    if (want_ws && split_tail && pm_ws_geometry(s, Rmax, Wmax, n_angles, a.max_rr, wg) &&
+    if (want_ws && split_tail && pm_ws_geometry(s, Rmax, Wmax, n_angles, a.max_rr, wg, 2 * typ_border + (Wmax - 2 * max_border) - s + 1) &&
         (size_t)wg.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows) &&
         make_window_tensor_map(ctx, &tmap1, wg.pbw, wg.pbh, 1))
         use_ws = true;

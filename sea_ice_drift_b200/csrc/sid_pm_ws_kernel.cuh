@@ -84,7 +84,7 @@ struct PmWsCfg {
     int off_a, off_tpl, tpl_buf_words, off_stat, stat_bytes, off_hs, off_c, smem_bytes;
 };
 
-inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, PmWsCfg &g) {
+inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, PmWsCfg &g, int Rtyp = 0) {
     if (s < 2 || s > 112 || Rmax < 2) return false;
     if (Rmax + 1 > 64 || Rmax + 15 > 64 || Wmax > 256) return false;
     g.nab = n_angles < 3 ? n_angles : 3;
@@ -110,6 +110,22 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     g.win_bytes = g.npanels * g.wrows * 16 + g.patch_bytes;
     g.hp = Wmax | 1;
     g.cpl = (max_rr + 31) & ~31;
+    {   // Pad the angle planes of the combined correlation buffer so that the epilogue's stores -- per instruction 4 adjacent x
+        // of 3 angles and 2 row parities (rows RW words apart) -- spread over the banks for the typical map width
+        // (measured: planes a multiple of 32 words apart made every store 3-way conflicted, 8 % of all shared wavefronts)
+        const int RW = Rtyp > 0 ? Rtyp : Rmax;
+        int best_pad = 0, best_worst = 99, best_distinct = 0;
+        for (int pad = 0; pad < 32; ++pad) {
+            int cnt[32] = {0}, worst = 0, distinct = 0;
+            for (int x = 0; x < 4; ++x) for (int aa = 0; aa < 3; ++aa) for (int ip = 0; ip < 2; ++ip) {
+                const int b = ((x + pad * aa - RW * ip) % 32 + 32) % 32;
+                if (++cnt[b] == 1) ++distinct;
+                if (cnt[b] > worst) worst = cnt[b];
+            }
+            if (worst < best_worst || (worst == best_worst && distinct > best_distinct)) { best_worst = worst; best_distinct = distinct; best_pad = pad; }
+        }
+        g.cpl += best_pad;
+    }
     g.inv_nw1 = (unsigned)((0x100000000ull + (unsigned)g.nwords) / (unsigned)(g.nwords + 1));
     g.tpl_buf_words = g.nab * s * g.tw;
     size_t off = (size_t)WS_NWIN * g.win_bytes;
@@ -689,21 +705,32 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                             if (--wleft == 0) { wp += PS - 16; wleft = 4; }
                         }
                     }
-                    // two byte streams: the column leaving the box and the column entering it
-                    const uint8_t *po = rowp + (c0 >> 4) * PS + (c0 & 15);
-                    int lo_left = 16 - (c0 & 15);
+                    // two byte streams -- the column leaving the box and the column entering it -- read as aligned words, four
+                    // columns per iteration (byte loads of 32 rows 16 bytes apart were 4-way bank conflicted: 13 % of all
+                    // shared-memory wavefronts of the kernel); the word one ahead is always inside the slot (x + s <= W, and the
+                    // staged panels are followed by the template patch)
                     const int c1 = c0 + s;
-                    const uint8_t *pi_ = rowp + (c1 >> 4) * PS + (c1 & 15);
-                    int li_left = 16 - (c1 & 15);
+                    const uint8_t *pwo = rowp + (c0 >> 4) * PS + (c0 & 12);
+                    const uint8_t *pwi = rowp + (c1 >> 4) * PS + (c1 & 12);
+                    int wo_left = 4 - ((c0 >> 2) & 3), wi_left = 4 - ((c1 >> 2) & 3);      // words left in the 16-byte panel row
+                    const unsigned sho = 8u * (unsigned)(c0 & 3), shi = 8u * (unsigned)(c1 & 3);
+                    uint32_t wo = *reinterpret_cast<const uint32_t *>(pwo), wi = *reinterpret_cast<const uint32_t *>(pwi);
                     uint16_t *hsp = hsT + xs * hp + r;
                     uint32_t *hqp = hqT + xs * hp + r;
-                    for (int x = xs; x < xe; ++x) {
-                        *hsp = (uint16_t)sum; *hqp = sq;
-                        hsp += hp; hqp += hp;
-                        const uint32_t va = *po++, vb = *pi_++;          // x + s <= W: the staged panels hold that column
-                        if (--lo_left == 0) { po += PS - 16; lo_left = 16; }
-                        if (--li_left == 0) { pi_ += PS - 16; li_left = 16; }
-                        sum += vb - va; sq += vb * vb - va * va;
+                    for (int x = xs; x < xe; x += 4) {
+                        pwo += 4; if (--wo_left == 0) { pwo += PS - 16; wo_left = 4; }
+                        pwi += 4; if (--wi_left == 0) { pwi += PS - 16; wi_left = 4; }
+                        const uint32_t wo2 = *reinterpret_cast<const uint32_t *>(pwo), wi2 = *reinterpret_cast<const uint32_t *>(pwi);
+                        const uint32_t out4 = __funnelshift_r(wo, wo2, sho), in4 = __funnelshift_r(wi, wi2, shi);
+                        wo = wo2; wi = wi2;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (x + j < xe) { *hsp = (uint16_t)sum; *hqp = sq; }
+                            hsp += hp; hqp += hp;
+                            const uint32_t va = (out4 >> (8 * j)) & 0xffu, vb = (in4 >> (8 * j)) & 0xffu;
+                            const uint32_t d = vb - va;
+                            sum += d; sq += d * (vb + va);
+                        }
                     }
                 }
             }
