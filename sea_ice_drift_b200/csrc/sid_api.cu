@@ -1334,17 +1334,17 @@ int sid_rotate_and_match(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1
     const size_t tpl_bytes = ((size_t)n_angles * s * s + 255) / 256 * 256;
     const size_t map_bytes = (rr * 4 + 255) / 256 * 256;
     const size_t small = 4096 + (size_t)n_angles * 64;
-    if ((rc = reserve(ctx, ctx->misc, 2 * int_bytes + tpl_bytes + 5 * map_bytes + small))) return rc;
+    if ((rc = reserve(ctx, ctx->misc, 2 * int_bytes + tpl_bytes + ((size_t)n_angles + 3) * map_bytes + small))) return rc;
     unsigned char *base = (unsigned char *)ctx->misc.p;
     uint32_t *d_isum = (uint32_t *)base, *d_isq = (uint32_t *)(base + int_bytes);
     uint8_t *d_tpl = base + 2 * int_bytes;
-    float *d_maps = (float *)(base + 2 * int_bytes + tpl_bytes);     // 0,1: ping-pong; 2,3,4: tmp_a, tmp_b, hes
-    unsigned char *sm = base + 2 * int_bytes + tpl_bytes + 5 * map_bytes;
+    float *d_maps = (float *)(base + 2 * int_bytes + tpl_bytes);     // one map per angle, then tmp_a, tmp_b, hes
+    unsigned char *sm = base + 2 * int_bytes + tpl_bytes + ((size_t)n_angles + 3) * map_bytes;
     double *d_tab = (double *)sm;                                     // n_angles * 4 doubles
     uint32_t *d_stats = (uint32_t *)(sm + (size_t)n_angles * 32);     // n_angles * 3
     uint32_t *d_ts = d_stats + (size_t)n_angles * 3 + 4;              // 2
-    unsigned long long *d_key = (unsigned long long *)(((uintptr_t)(d_ts + 4) + 15) & ~(uintptr_t)15);
-    float *d_peak = (float *)(d_key + 2);
+    unsigned long long *d_key = (unsigned long long *)(((uintptr_t)(d_ts + 4) + 15) & ~(uintptr_t)15);   // one per angle
+    float *d_peak = (float *)(d_key + n_angles + 1);
     const size_t mstride = map_bytes / 4;
 
     CU(cudaMemcpyAsync(d_tab, angle_tab, (size_t)n_angles * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -1362,32 +1362,36 @@ int sid_rotate_and_match(sid_ctx *ctx, const uint8_t *img1, int rows1, int cols1
         *dc = NAN; *dr = NAN; *best_angle_idx = -1; *best_r = NAN; *best_h = NAN;
         return SID_OK;
     }
-    float br = -INFINITY; int ba = -1, bslot = -1; uint32_t bidx = 0;
+    // every angle's map and arg-max are enqueued back to back; ONE read-back of the keys decides the winner (strict '>' in
+    // angle order, like the reference loop pmlib.py:155-166)
     for (int a = 0; a < n_angles; ++a) {
-        const int slot = (bslot == 0) ? 1 : 0;
-        float *d_map = d_maps + (size_t)slot * mstride;
+        float *d_map = d_maps + (size_t)a * mstride;
         rc = match_on_device(ctx, (const uint8_t *)ctx->img2.p, H, W, dp2, d_tpl + (size_t)a * s * s, s, s, s,
                              d_isum, d_isq, a > 0, d_ts, d_map);
         if (rc) return rc;
-        argmax_kernel<<<1, 1024, 0, ctx->stream>>>(d_map, (int)rr, d_key);
+        argmax_kernel<<<1, 1024, 0, ctx->stream>>>(d_map, (int)rr, d_key + a);
         ctx->launches += 1;
-        unsigned long long key = 0;
-        CU(cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        CU(cudaGetLastError());
+    }
+    std::vector<unsigned long long> keys((size_t)n_angles, 0ull);
+    CU(cudaMemcpyAsync(keys.data(), d_key, (size_t)n_angles * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    float br = -INFINITY; int ba = -1; uint32_t bidx = 0;
+    for (int a = 0; a < n_angles; ++a) {
+        const unsigned long long key = keys[(size_t)a];
         const uint32_t hi = (uint32_t)(key >> 32);
         const uint32_t ubits = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
         float v; memcpy(&v, &ubits, 4);
-        if (v > br) { br = v; ba = a; bslot = slot; bidx = 0xffffffffu - (uint32_t)(key & 0xffffffffull); }
+        if (v > br) { br = v; ba = a; bidx = 0xffffffffu - (uint32_t)(key & 0xffffffffull); }
     }
     if (ba < 0) {
         *valid = 0; *dc = NAN; *dr = NAN; *best_angle_idx = -1; *best_r = NAN; *best_h = NAN;
         return SID_OK;
     }
     PeakArgs pa;
-    pa.best = d_maps + (size_t)bslot * mstride; pa.rows = RH; pa.cols = RW; pa.idx = (int)bidx; pa.r = br; pa.flags = flags;
+    pa.best = d_maps + (size_t)ba * mstride; pa.rows = RH; pa.cols = RW; pa.idx = (int)bidx; pa.r = br; pa.flags = flags;
     gaussian_weights(pa.gw);
-    pa.tmp_a = d_maps + 2 * mstride; pa.tmp_b = d_maps + 3 * mstride; pa.hes = d_maps + 4 * mstride; pa.out = d_peak;
+    pa.tmp_a = d_maps + (size_t)n_angles * mstride; pa.tmp_b = pa.tmp_a + mstride; pa.hes = pa.tmp_b + mstride; pa.out = d_peak;
     peak_stats_kernel<<<1, 1024, 0, ctx->stream>>>(pa);
     ctx->launches += 1;
     float hp[2];
