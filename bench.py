@@ -437,9 +437,12 @@ def main_ours(args):
         sm_max = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
         peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
         achieved = flops_step / (kernel_ms * 1e-3) / 1e12
-        traffic = None
+        traffic = traffic_by_kernel = traffic_algorithmic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(args.workload)
+            traffic_by_kernel = tj.get(args.workload + "_by_kernel")
+            traffic_algorithmic = tj.get(args.workload + "_algorithmic")
         except (OSError, ValueError):
             pass
         tensor_peak = float(peaks.get("bf16_tflops") or 1590.0)
@@ -453,6 +456,9 @@ def main_ours(args):
         # bounding roofline is "tensor" against the measured dense bf16 peak of MEASURED_PEAKS.json
         roofline = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                     "frac": achieved / tensor_peak, "traffic": traffic,
+                    "traffic_by_kernel": traffic_by_kernel, "traffic_algorithmic": traffic_algorithmic,
+                    "traffic_note": "DRAM bytes of one step = both kernels (ncu --set full, profiles/traffic.json); the excess over the "
+                                    "algorithmic bytes is the winning-map hand-off to pm_tail_kernel; HBM is < 4 % busy",
                     "kernel": kernel_name, "kernel_ms": kernel_ms, "step_ms": ms_per_step,
                     "kernels_per_step": "%s (correlation on tcgen05.mma kind::i8, dominant) + pm_tail_kernel (peak statistics)"
                                         % kernel_name.split("::")[-1],

@@ -769,8 +769,12 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                     double d[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int idx = min(base + WS_NST * c + st_, RR - 1);
-                        d[c] = window_den(wsum[idx], wsq2[2 * idx], a.inv_area);
+                        // past the end: zeros, not a clamped index -- another thread may already have overwritten that slot's
+                        // sum of squares with its denominator (the value would be unused, but it is a read-write race)
+                        const int idx = base + WS_NST * c + st_;
+                        uint32_t vs = 0u, vq = 0u;
+                        if (idx < RR) { vs = wsum[idx]; vq = wsq2[2 * idx]; }
+                        d[c] = window_den(vs, vq, a.inv_area);
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
