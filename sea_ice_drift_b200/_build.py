@@ -31,14 +31,27 @@ def build(force=False, verbose=False, out=None, extra=()):
     ``build(force=True, out='/tmp/libsid_variant.so', extra=['-DSOME_SWITCH'])`` for an A/B run."""
     if not force and not is_stale() and out is None:
         return LIB
-    cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", out or LIB, os.path.join(CSRC, "sid_api.cu")]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode:
-        sys.stderr.write(res.stdout)
-    if res.returncode:
-        raise RuntimeError("nvcc failed (%d)" % res.returncode)
-    return out or LIB
+    target = out or LIB
+    # several ranks of one torchrun may find the library stale at the same moment: one builds (file lock), the others
+    # wait and re-check; the compiler writes to a temporary name and the result is moved into place atomically, so a
+    # concurrent loader never sees a half-written file
+    import fcntl
+    with open(target + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and out is None and not is_stale():
+            return LIB
+        tmp = "%s.tmp.%d" % (target, os.getpid())
+        cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-o", tmp, os.path.join(CSRC, "sid_api.cu")]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or res.returncode:
+            sys.stderr.write(res.stdout)
+        if res.returncode:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed (%d)" % res.returncode)
+        os.replace(tmp, target)
+    return target
 
 
 if __name__ == "__main__":

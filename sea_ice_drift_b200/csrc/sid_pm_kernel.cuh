@@ -735,7 +735,7 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
 // histogram; a third sweep collects the (<= 64) values sharing the median's upper 20 bits.  hypot() is never negative, so a
 // value's bit pattern is its sortable key (digits: bits 30..21 | 20..11 | 10..0).  The sums are exact in FP64 for maps of
 // this size whatever the order (24-bit addends, < 2^11 of them, exponent spread < 2^17), which is why the fused kernels,
-// this path and the CPU oracle agree bit for bit.
+// this path and the CPU restatement used by the tests agree bit for bit.
 // Rank search over 1024 bins (8 per thread): the thread owning the bin of rank kk writes sel = {bin, rank inside it,
 // population of the bin, 0}.  Two barriers inside.
 __device__ __forceinline__ void tail_rank_search(const uint32_t *__restrict__ hist, uint32_t kk, BlockScratch &bs) {
