@@ -388,10 +388,17 @@ def main_ours(args):
                 cc["side"] = args.side if name != "cfg1" else min(args.side, cc["side"])
             if args.grid:
                 cc["grid"] = args.grid
+            fg_note = None
             if name == "cfg1":
                 i1, i2, q1, q2, q3, q4, q5, cc2 = syn.make_config("cfg1", seed=0, side=cc["side"], grid=cc["grid"])
-                ctx.set_pair(i1, i2)
                 cpts = [q1, q2, q3, q4, q5]
+                try:        # BASELINE configs[0] says "ORB first guess": borders from a real one (outside the timed region)
+                    cpts = list(syn.orb_first_guess_inputs(i1, i2, cc["grid"], cc["img_size"]))
+                    fg_note = ("ORB first guess (cv2.ORB + GPU Hamming matcher + prepare_first_guess): borders %d..%d, %.0f %% at %d"
+                               % (cpts[4].min(), cpts[4].max(), 100.0 * (cpts[4] == cpts[4].min()).mean(), cpts[4].min()))
+                except Exception as exc:        # no cv2 on the box: the seeded random borders of synthetic.make_config
+                    fg_note = "random borders 20..50 (ORB first guess unavailable: %s)" % type(exc).__name__
+                ctx.set_pair(i1, i2)
             else:       # cfg3 / cfg4 use the EW pair that is already resident (same seed, same warp)
                 m = syn.rotation_matrix(img1.shape, cc["warp"][1])
                 cpts = list(syn.hot_loop_inputs(img1, m, cc["grid"], cc["img_size"], cc["border"], rank))
@@ -399,8 +406,10 @@ def main_ours(args):
             fl = float(flops_per_point(cc["img_size"], cpts[4][st_c == 1], len(cc["angles"])).sum())
             configs[name] = {"workload": workload_description(name, cc, len(cpts[0])), "points": int(len(cpts[0])),
                              "valid": int((st_c == 1).sum()), "value": len(cpts[0]) / (ms_c * 1e-3), "unit": UNIT,
-                             "ms_per_step": ms_c, "kernel_ms": k_ms, "steps": steps_c,
+                             "ms_per_step": ms_c, "kernel_ms": k_ms, "steps": steps_c, "kernel": ctx.last_kernel_name,
                              "tflops_equiv": fl / (k_ms * 1e-3) / 1e12}
+            if fg_note:
+                configs[name]["first_guess"] = fg_note
         ctx.set_stream(None)
         ctx.set_pair(img1p, img2p)
 

@@ -63,6 +63,8 @@ struct sid_ctx {
     cudaEvent_t k_ev[2] = {};                // bracket the last fused-kernel launch (sid_last_kernel_ms)
     bool k_ev_valid = false;
     const char *k_name = "";
+    bool k_ev_hold = false;                  // second launch of a two-class call: keep the start event of the first
+    size_t tail_region_stride = 0;           // floats per point of the tail-map regions of the current host call (0: the launch's own)
     long long table_n = -1;                  // rows of the result table the last sid_run / sid_run_pair left in `out`
     long long tail_hint_n = 0;               // total points of the current host call (sizes the tail hand-off once)
     // staged upload of pageable host images (sid_run_pair): pinned double buffer + "slot free again" events
@@ -244,9 +246,11 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         a.split_tail = 1;
         const size_t cap_n = (size_t)std::max<long long>(n + tail_off, ctx->tail_hint_n);
         a.tail_stride = (a.max_rr + 3) & ~3;
-        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.tail_stride * sizeof(float)))) return rc;
+        // regions of concurrently running launches (bands, border classes) are laid out with ONE stride per host call
+        const size_t region_stride = std::max(ctx->tail_region_stride, (size_t)a.tail_stride);
+        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * region_stride * sizeof(float)))) return rc;
         if ((rc = reserve(ctx, ctx->tail_recs, cap_n * sizeof(PmTailRec)))) return rc;
-        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.tail_stride;
+        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * region_stride;
         a.tail_recs = (PmTailRec *)ctx->tail_recs.p + tail_off;
         const void *kfn = (const void *)pm_ws_kernel;
         if (int arc = allow_max_smem(ctx, kfn)) return arc;
@@ -263,11 +267,13 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
 #endif
         void *params_ws[] = {(void *)&a, (void *)&wg, (void *)&tmap, (void *)&tmap1};
         if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
-        CU(cudaEventRecord(ctx->k_ev[0], st));
+        if (!ctx->k_ev_hold) CU(cudaEventRecord(ctx->k_ev[0], st));
         CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)WS_THREADS), params_ws, (size_t)wg.smem_bytes, st));
         CU(cudaEventRecord(ctx->k_ev[1], st));
         ctx->k_ev_valid = true;
-        ctx->k_name = "sid::pm_ws_kernel";
+        ctx->k_name = !ctx->k_ev_hold ? "sid::pm_ws_kernel"
+                      : strstr(ctx->k_name, "pm_tc_kernel") ? "sid::pm_tc_kernel + sid::pm_ws_kernel"
+                      : strstr(ctx->k_name, "pm_points_kernel") ? "sid::pm_points_kernel + sid::pm_ws_kernel" : "sid::pm_ws_kernel";
         ctx->launches += 1;
 #ifdef SID_WS_PROF
         {
@@ -455,16 +461,17 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     if (split_tail) {
         const size_t cap_n = (size_t)std::max<long long>(n + tail_off, ctx->tail_hint_n);
         a.tail_stride = (a.max_rr + 3) & ~3;
-        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * a.tail_stride * sizeof(float)))) return rc;
+        const size_t region_stride = std::max(ctx->tail_region_stride, (size_t)a.tail_stride);
+        if ((rc = reserve(ctx, ctx->tail_maps, cap_n * region_stride * sizeof(float)))) return rc;
         if ((rc = reserve(ctx, ctx->tail_recs, cap_n * sizeof(PmTailRec)))) return rc;
-        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * a.tail_stride;
+        a.tail_maps = (float *)ctx->tail_maps.p + (size_t)tail_off * region_stride;
         a.tail_recs = (PmTailRec *)ctx->tail_recs.p + tail_off;
     }
     void *params_legacy[] = {(void *)&a, (void *)&tmap};
     void *params_tc[] = {(void *)&a, (void *)&tg, (void *)&tmap};
     void **params = use_tc ? params_tc : params_legacy;
     if (!ctx->k_ev[0]) { CU(cudaEventCreate(&ctx->k_ev[0])); CU(cudaEventCreate(&ctx->k_ev[1])); }
-    CU(cudaEventRecord(ctx->k_ev[0], st));
+    if (!ctx->k_ev_hold) CU(cudaEventRecord(ctx->k_ev[0], st));
     CU(cudaLaunchKernel(kfn, dim3((unsigned)grid), dim3((unsigned)threads), params, smem, st));
     CU(cudaEventRecord(ctx->k_ev[1], st));
     ctx->k_ev_valid = true;
@@ -639,6 +646,57 @@ static int upload_angles(sid_ctx *ctx, int n_angles, const double *angles, const
 }
 
 namespace {
+
+// Largest border (<= max_border) for which launch_pm would pick pm_ws_kernel (its geometry, its shared-memory layout and
+// the split tail all fit); -1 if none.  Used to send the points of a call to the kernels by border class.
+int ws_border_limit(sid_ctx *ctx, int s, int n_angles, unsigned flags, int max_border) {
+    const char *path_env = getenv("SID_PM_PATH");
+    const bool want_ws = path_env ? strcmp(path_env, "ws") == 0 : SID_WS_DEFAULT != 0;
+    if (!want_ws) return -1;
+    if (const char *e = getenv("SID_PM_SPLIT_TAIL")) if (e[0] == '0') return -1;
+    const bool smth = (flags & SID_HES_SMTH) != 0;
+    const int hws = s / 2;
+    for (int b = std::min(max_border, 40); b >= 1; --b) {
+        const int Wmax = 2 * hws + 2 * b + 1, Rmax = Wmax - s + 1;
+        if (Rmax < 2) break;
+        if (pm_tail_smem_bytes(Rmax * Rmax, smth) > 52 * 1024) continue;
+        PmWsCfg g;
+        memset(&g, 0, sizeof g);
+        // the launch pads the angle planes for ITS typical map width (<= 31 words each): try the worst case, so that a
+        // border this function accepts is never refused by the launch
+        bool ok = pm_ws_geometry(s, Rmax, Wmax, n_angles, Rmax * Rmax, g) && (size_t)g.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin;
+        if (ok && (size_t)g.smem_bytes + 2048 + 31 * 4 * 2 * 3 > (size_t)ctx->max_smem_optin) {
+            for (int rt = 2; rt <= Rmax && ok; ++rt)
+                ok = pm_ws_geometry(s, Rmax, Wmax, n_angles, Rmax * Rmax, g, rt) && (size_t)g.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin;
+        }
+        if (ok) return b;
+    }
+    return -1;
+}
+
+// Device-resident callers (sid_run_device): split the point indices by border class on the device
+__global__ void partition_by_border_kernel(const double *__restrict__ border, int n, int limit, int *__restrict__ order_small,
+                                           int *__restrict__ order_big, unsigned *__restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool small = false, valid = i < n;
+    if (valid) {
+        const double b = border[i];
+        int v = 0;
+        if (isfinite(b) && b >= 0.0 && b < 4096.0) v = (int)ceil(b);
+        small = v <= limit;
+    }
+    const unsigned m_small = __ballot_sync(0xffffffffu, valid && small), m_big = __ballot_sync(0xffffffffu, valid && !small);
+    const int lane = threadIdx.x & 31;
+    unsigned base_s = 0, base_b = 0;
+    if (lane == 0) {
+        if (m_small) base_s = atomicAdd(&counts[0], (unsigned)__popc(m_small));
+        if (m_big) base_b = atomicAdd(&counts[1], (unsigned)__popc(m_big));
+    }
+    base_s = __shfl_sync(0xffffffffu, base_s, 0); base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (valid && small) order_small[base_s + __popc(m_small & below)] = i;
+    if (valid && !small) order_big[base_b + __popc(m_big & below)] = i;
+}
 
 // true when `p` is ordinary pageable host memory (cudaMemcpyAsync from it is a slow, synchronous staged copy)
 bool is_pageable(const void *p) {
@@ -830,13 +888,39 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
     for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
     std::vector<int> band_start((size_t)nbands + 1, 0);
     for (int k = 0; k <= nbands; ++k) band_start[(size_t)k] = hist[std::min(nkeys, (size_t)k * (size_t)(max_border + 1))];
-    int typ_border = max_border;
-    {   // median border = typical point
-        std::vector<long long> per_b((size_t)max_border + 1, 0);
-        for (int64_t i = 0; i < n; ++i) ++per_b[(size_t)ib[(size_t)i]];
-        long long acc = 0;
-        for (int b = max_border; b >= 0; --b) { acc += per_b[(size_t)b]; if (acc > n / 2) { typ_border = b; break; } }
+    std::vector<long long> per_b((size_t)max_border + 1, 0);
+    for (int64_t i = 0; i < n; ++i) ++per_b[(size_t)ib[(size_t)i]];
+    auto median_border = [&](int b_lo, int b_hi) {          // median of the borders in [b_lo, b_hi] = the typical point of a class
+        long long total = 0, acc = 0;
+        for (int b = b_lo; b <= b_hi; ++b) total += per_b[(size_t)b];
+        for (int b = b_hi; b >= b_lo; --b) { acc += per_b[(size_t)b]; if (2 * acc > total) return b; }
+        return b_hi;
+    };
+    int typ_border = median_border(0, max_border);
+    // ---- border classes.  A launch is sized by its largest border, and the fastest kernel (pm_ws_kernel) only takes small
+    //      result maps: with the reference's default borders (20 ... 50 by the distance to the nearest keypoint,
+    //      pmlib.py:315-322) most points sit at the minimum -- 86 % of BASELINE configs[0]'s grid with a real ORB first
+    //      guess -- and a few far from any keypoint would drag the whole call onto the kernels for large maps.  So the points
+    //      whose border fits pm_ws_kernel get their own launch per band, behind the larger ones (SID_PM_CLASSES=0: one launch).
+    int small_max = -1, typ_small = 0, typ_big = typ_border;
+    bool two_class = false;
+    {
+        const char *e = getenv("SID_PM_CLASSES");
+        const int limit = (e && e[0] == '0') ? -1 : ws_border_limit(ctx, img_size, n_angles, flags, max_border);
+        if (limit >= 0 && limit < max_border) {
+            long long n_small = 0;
+            for (int b = 0; b <= limit; ++b) if (per_b[(size_t)b]) { n_small += per_b[(size_t)b]; small_max = b; }
+            if (n_small >= 256 && small_max >= 1) {
+                two_class = true;
+                typ_small = median_border(0, small_max);
+                typ_big = median_border(limit + 1, max_border);
+            }
+        }
     }
+    std::vector<int> band_mid((size_t)nbands, 0);           // first point of the small class inside each band's range
+    for (int k = 0; k < nbands; ++k)
+        band_mid[(size_t)k] = two_class ? hist[(size_t)k * (size_t)(max_border + 1) + (size_t)(max_border - small_max)]
+                                        : band_start[(size_t)k + 1];
 
     const size_t pts_bytes = (size_t)n * 5 * sizeof(double);
     const size_t ord_bytes = (size_t)n * sizeof(int);
@@ -873,6 +957,14 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
 
     const double *dp = (const double *)ctx->pts.p;
     ctx->tail_hint_n = n;
+    ctx->tail_region_stride = 0;
+    if (two_class) {
+        // one stride for the tail-map regions of both classes (launches of different bands run concurrently)
+        auto rr_of = [&](int b) { const int R = 2 * (img_size / 2) + 2 * b + 1 - img_size + 1; return R * R; };
+        const bool smth = (flags & SID_HES_SMTH) != 0;
+        const int rr_big = rr_of(max_border), rr_small = rr_of(small_max);
+        ctx->tail_region_stride = (size_t)(((pm_tail_smem_bytes(rr_big, smth) <= 52 * 1024 ? rr_big : rr_small) + 3) & ~3);
+    }
     const bool two_streams = pair && nbands > 1;
     if (two_streams) {
         if (!ctx->band_stream[0])
@@ -886,13 +978,24 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
         // consecutive bands go to alternating streams: the next band's CTAs fill the SMs while this one drains
         cudaStream_t st = two_streams ? ctx->band_stream[k & 1] : ctx->stream;
         if (pair) CU(cudaStreamWaitEvent(st, ctx->band_event[k], 0));
-        const int lo = band_start[(size_t)k], hi = band_start[(size_t)k + 1];
+        const int lo = band_start[(size_t)k], hi = band_start[(size_t)k + 1], mid = band_mid[(size_t)k];
         if (hi <= lo) continue;
-        rc = launch_pm(ctx, hi - lo, dp, dp + n, dp + 2 * n, dp + 3 * n, dp + 4 * n, (const int *)ctx->order.p + lo,
-                       max_border, typ_border, img_size, n_angles, d_angles, d_tab, rot_order, flags,
-                       (double *)ctx->out.p, (int *)ctx->status.p, st, two_streams ? (k & 1) : 0, lo);
-        if (rc) return rc;
+        if (mid > lo) {         // the larger borders (all points when the call is not split into classes)
+            rc = launch_pm(ctx, mid - lo, dp, dp + n, dp + 2 * n, dp + 3 * n, dp + 4 * n, (const int *)ctx->order.p + lo,
+                           max_border, two_class ? typ_big : typ_border, img_size, n_angles, d_angles, d_tab, rot_order, flags,
+                           (double *)ctx->out.p, (int *)ctx->status.p, st, two_streams ? (k & 1) : 0, lo);
+            if (rc) { ctx->tail_region_stride = 0; return rc; }
+        }
+        if (hi > mid) {         // the class of pm_ws_kernel
+            ctx->k_ev_hold = mid > lo;
+            rc = launch_pm(ctx, hi - mid, dp, dp + n, dp + 2 * n, dp + 3 * n, dp + 4 * n, (const int *)ctx->order.p + mid,
+                           small_max, typ_small, img_size, n_angles, d_angles, d_tab, rot_order, flags,
+                           (double *)ctx->out.p, (int *)ctx->status.p, st, two_streams ? (k & 1) : 0, mid);
+            ctx->k_ev_hold = false;
+            if (rc) { ctx->tail_region_stride = 0; return rc; }
+        }
     }
+    ctx->tail_region_stride = 0;
     if (two_streams) {
         for (int k = 0; k < 2; ++k) {
             CU(cudaEventRecord(ctx->slot_event[1 + k], ctx->band_stream[k]));
@@ -952,6 +1055,41 @@ int sid_run_device(sid_ctx *ctx, int64_t n, const double *d_c1, const double *d_
     }
     const double *d_angles, *d_tab;
     if ((rc = upload_angles(ctx, n_angles, angles, angle_tab, &d_angles, &d_tab))) return rc;
+    ctx->tail_region_stride = 0;
+    // border classes as in sid_run (see run_host): the indices are split on the device, one 8-byte read-back sizes the launches
+    const char *ce = getenv("SID_PM_CLASSES");
+    const int limit = (ce && ce[0] == '0') || n < 512 ? -1 : ws_border_limit(ctx, img_size, n_angles, flags, max_border);
+    if (limit >= 0 && limit < max_border) {
+        if ((rc = reserve(ctx, ctx->order, (size_t)n * 2 * sizeof(int) + 64))) return rc;
+        int *d_small = (int *)ctx->order.p, *d_big = d_small + n;
+        unsigned *d_counts = (unsigned *)(d_big + n);
+        CU(cudaMemsetAsync(d_counts, 0, 8, ctx->stream));
+        partition_by_border_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_border, (int)n, limit, d_small, d_big, d_counts);
+        ctx->launches += 1;
+        unsigned counts[2] = {0, 0};
+        CU(cudaMemcpyAsync(counts, d_counts, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaGetLastError());
+        const long long n_small = counts[0], n_big = counts[1];
+        if (n_small >= 256 && n_big > 0) {
+            auto rr_of = [&](int b) { const int R = 2 * (img_size / 2) + 2 * b + 1 - img_size + 1; return R * R; };
+            const bool smth = (flags & SID_HES_SMTH) != 0;
+            ctx->tail_region_stride = (size_t)(((pm_tail_smem_bytes(rr_of(max_border), smth) <= 52 * 1024 ? rr_of(max_border) : rr_of(limit)) + 3) & ~3);
+            ctx->tail_hint_n = n;
+            rc = launch_pm(ctx, n_big, d_c1, d_r1, d_c2fg, d_r2fg, d_border, d_big, max_border, max_border, img_size,
+                           n_angles, d_angles, d_tab, rot_order, flags, d_out, d_status, nullptr, 0, 0);
+            if (!rc) {
+                ctx->k_ev_hold = true;
+                rc = launch_pm(ctx, n_small, d_c1, d_r1, d_c2fg, d_r2fg, d_border, d_small, limit, limit, img_size,
+                               n_angles, d_angles, d_tab, rot_order, flags, d_out, d_status, nullptr, 0, n_big);
+                ctx->k_ev_hold = false;
+            }
+            ctx->tail_region_stride = 0;
+            ctx->tail_hint_n = 0;
+            return rc;
+        }
+        if (n_big == 0) max_border = limit;              // every point fits the pipeline kernel
+    }
     return launch_pm(ctx, n, d_c1, d_r1, d_c2fg, d_r2fg, d_border, nullptr, max_border, max_border, img_size,
                      n_angles, d_angles, d_tab, rot_order, flags, d_out, d_status);
 }

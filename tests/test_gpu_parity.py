@@ -506,6 +506,45 @@ def test_warp_specialised_kernel_is_the_default_for_small_search_radii(gpu_ctx):
         assert np.array_equal(default, legacy, equal_nan=True), border
 
 
+def test_border_classes_send_small_maps_to_the_pipeline_kernel(gpu_ctx):
+    """Borders as prepare_first_guess produces them (most points at the minimum of 20, a tail up to 45): the call is split
+    into two launches per band -- the larger maps on the row-loop / mma.sync kernels, the rest on pm_ws_kernel -- and the
+    table is bit for bit the single-launch one (SID_PM_CLASSES=0), resident and through the banded upload."""
+    img1, img2, c1, r1, c2, r2, b, cfg = syn.make_config("cfg2", seed=41, side=2600, grid=40)
+    rng = np.random.default_rng(8)
+    brd = np.where(rng.random(len(c1)) < 0.86, 20.0, np.floor(rng.uniform(21, 46, len(c1))))
+    brd[::97] = 20.5                                     # fractional borders: ceil() decides the class, the kernel the window
+    assert (brd == 20).sum() > 1000 and brd.max() >= 44
+    gpu_ctx.set_pair(img1, img2)
+    for angles in ([-3, 0, 3], [0]):
+        split, st_split = gpu_ctx.run(c1, r1, c2, r2, brd, 35, angles, 0.5, want_status=True)
+        assert gpu_ctx.last_kernel_name.endswith("+ sid::pm_ws_kernel"), gpu_ctx.last_kernel_name
+        os.environ["SID_PM_CLASSES"] = "0"
+        try:
+            single, st_single = gpu_ctx.run(c1, r1, c2, r2, brd, 35, angles, 0.5, want_status=True)
+            assert "pm_ws_kernel" not in gpu_ctx.last_kernel_name
+        finally:
+            del os.environ["SID_PM_CLASSES"]
+        assert np.array_equal(split, single, equal_nan=True) and np.array_equal(st_split, st_single)
+        assert np.isfinite(split[:, 0]).sum() > 1400
+    banded = gpu_ctx.run_pair(img1, img2, c1, r1, c2, r2, brd, 35, [0], 0.5)
+    assert np.array_equal(banded, single, equal_nan=True)
+    # device-resident point arrays (sid_run_device): the indices are split on the device
+    import torch
+    dev = torch.device("cuda", gpu_ctx.device)
+    d_pts = torch.from_numpy(np.stack([c1, r1, c2, r2, brd])).to(dev)
+    d_out = torch.full((len(c1), 5), -7.0, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.run_device(len(c1), *[d_pts[k].data_ptr() for k in range(5)], int(brd.max()), 35, [0], 0.5, d_out.data_ptr())
+    assert gpu_ctx.last_kernel_name.endswith("+ sid::pm_ws_kernel"), gpu_ctx.last_kernel_name
+    gpu_ctx.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), single, equal_nan=True)
+    # too few small-map points for a launch of their own: one class
+    few = np.where(np.arange(len(c1)) < 100, 20.0, 30.0)
+    gpu_ctx.run(c1, r1, c2, r2, few, 35, [0], 0.5)
+    assert "+" not in gpu_ctx.last_kernel_name
+
+
 def test_device_epilogue_equals_host_post_processing():
     """remainder add, pixel -> x/y / lon/lat, u/v differences and the _fill_gpi scatter on the device
     (sid_pm_epilogue_affine, table kept on the device) give the same seven grids, bit for bit, as the host lines that
