@@ -15,7 +15,11 @@ One step = one pass of the hot path over the whole PM grid of one image pair.
             over the kernel's average duration, against the measured dense tensor peak of
             MEASURED_PEAKS.json (the multiply-adds run as tcgen05 kind::i8 MMAs); roofline_fma repeats it
             against the FP32-FMA peak that BASELINE.json's metric names.
-  configs : the other single-GPU BASELINE configurations (cfg1, cfg3, cfg4) at full size, device-resident.
+  configs : the other single-GPU BASELINE configurations (cfg1, cfg3, cfg4) at full size, device-resident; cfg1 with the
+            borders of a real ORB first guess.
+  drop_in : the whole call a user of the reference makes -- pattern_matching(lon, lat, n1, x1, y1, n2, x2, y2) on
+            configs[0] with NumPy images -- wall clock, next to the UNMODIFIED reference's pattern_matching on the same
+            inputs (its own ORB matches; timed in a child process before CUDA is initialised).
   cpu_baseline / --impl reference: the UNMODIFIED reference's own per-point loop (pmlib.use_mcc_mp through a
             fork Pool over all host cores, from the oracle/_ref copy placed by oracle/build_ref.py; kind
             "reference") on a bounded sample of the same workload -- the NumPy/cv2/scipy port
@@ -57,6 +61,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg1 / cfg3 / cfg4 block")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block at N > 1")
+    ap.add_argument("--drop-in-reference", default="", metavar="NPZ",
+                    help="(internal, child process) time the reference's own pattern_matching on configs[0] and save the matches")
     return ap.parse_args()
 
 
@@ -140,6 +146,84 @@ def cpu_port_rate(pts, img1, img2, img_size, angles, sample, threads, seed=0):
         rows = pm_oracle.run_points(*sub, img1, img2, img_size, 0.0, threads=threads, angles=angles)
     dt = time.perf_counter() - t0
     return len(sel) / dt, len(sel), dt, rows, sel
+
+
+DROP_IN = dict(side=2000, grid=50, img_size=35, angles=[0])
+
+
+def drop_in_scene(syn):
+    """BASELINE configs[0] for the whole drop-in call: the pair, its affine domains and the 50 x 50 lon / lat grid."""
+    img1, img2, _, _, _, _, _, _ = syn.make_config("cfg1", seed=0, side=DROP_IN["side"])
+    n1, n2 = syn.ArrayDomain(img1), syn.ArrayDomain(img2)
+    gx, gy = np.meshgrid(np.linspace(100, DROP_IN["side"] - 100, DROP_IN["grid"]), np.linspace(100, DROP_IN["side"] - 100, DROP_IN["grid"]))
+    lon, lat = n2.transform_points(gx, gy)
+    return img1, img2, n1, n2, lon, lat
+
+
+def drop_in_reference_child(path):
+    """Child process (no CUDA): the UNMODIFIED reference end to end on configs[0] -- its own ORB feature tracking
+    (find_key_points / get_match_coords / lstsq_filter), then its pattern_matching (prepare_first_guess + fork Pool over
+    use_mcc_mp + post-processing) on all host cores.  Saves the matches for the product's run; prints one JSON line."""
+    import contextlib
+    import io
+    from sea_ice_drift_b200 import synthetic as syn
+    from oracle import ref_runner
+    img1, img2, n1, n2, lon, lat = drop_in_scene(syn)
+    x1, y1, x2, y2 = ref_runner.orb_first_guess(img1, img2)
+    np.savez(path, x1=x1, y1=y1, x2=x2, y2=y2)
+    pm = ref_runner.reference_module()
+    import nansat
+    nansat.NSR = lambda srs=None: srs
+    pm.NSR = nansat.NSR
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = pm.pattern_matching(lon, lat, n1, x1, y1, n2, x2, y2, threads=threads, angles=DROP_IN["angles"], img_size=DROP_IN["img_size"])
+    dt = time.perf_counter() - t0
+    print(json.dumps({"seconds": dt, "threads": threads, "valid": int(np.isfinite(res[0]).sum()), "matches": int(len(x1)),
+                      "checksum": float(np.nansum(np.abs(res[0])) + np.nansum(np.abs(res[1])) + np.nansum(res[2]))}), flush=True)
+    return 0
+
+
+def drop_in_block(syn, ref_line):
+    """The call a user of the reference makes -- pattern_matching(lon, lat, n1, x1, y1, n2, x2, y2) on configs[0] with
+    plain NumPy images -- timed end to end (first guess on the device, upload, matching, post-processing epilogue),
+    next to the unmodified reference on the same inputs (timed by the child process before CUDA was initialised)."""
+    import contextlib
+    import io
+    from sea_ice_drift_b200 import pmlib
+    m = np.load(ref_line["npz"])
+    img1, img2, n1, n2, lon, lat = drop_in_scene(syn)
+    kw = dict(angles=DROP_IN["angles"], img_size=DROP_IN["img_size"])
+
+    def checksum(res):      # u, v (displacements) and the winning angles summed: equal to 1e-9 relative means the same vectors
+        return float(np.nansum(np.abs(res[0])) + np.nansum(np.abs(res[1])) + np.nansum(res[2]))
+
+    def timed(**extra):
+        ts, res = [], None
+        for _ in range(6):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                res = pmlib.pattern_matching(lon, lat, n1, m["x1"], m["y1"], n2, m["x2"], m["y2"], **kw, **extra)
+            ts.append(time.perf_counter() - t0)
+        same = bool(int(np.isfinite(res[0]).sum()) == ref_line["valid"] and
+                    abs(checksum(res) - ref_line["checksum"]) <= 1e-9 * max(1.0, abs(ref_line["checksum"])))
+        return float(np.median(ts[1:])), ts[0], int(np.isfinite(res[0]).sum()), same
+
+    mine, first, valid, same = timed()
+    dev, _, valid_dev, same_dev = timed(first_guess="device")
+    return {"call": "pattern_matching(lon, lat, n1, x1, y1, n2, x2, y2, angles=[0], img_size=35) on configs[0]: 2000 x 2000 pair, "
+                    "%d ORB matches (the reference's own feature tracking), 50 x 50 grid; NumPy images in, seven (50, 50) grids out"
+                    % ref_line["matches"],
+            "ms": mine * 1e3, "first_call_ms": first * 1e3, "vectors_per_s": valid / mine, "valid": valid,
+            "reference_s": ref_line["seconds"], "reference_threads": ref_line["threads"], "reference_valid": ref_line["valid"],
+            "speedup": ref_line["seconds"] / mine, "same_vectors": same,
+            "ms_first_guess_device": dev * 1e3, "speedup_first_guess_device": ref_line["seconds"] / dev,
+            "same_vectors_first_guess_device": same_dev,
+            "note": "default first_guess='auto': ORB keypoints of pyramid level 0 are integer pixels, so under this scene's identity "
+                    "geolocation some Delaunay cells are cocircular and the triangulation is not unique; 'auto' detects that and takes "
+                    "the SciPy / Qhull path (~85 ms of the call) so that the first guess is the reference's in every case. Keypoints in "
+                    "generic position (any real geolocation) and first_guess='device' use the triangulation-free device interpolant"}
 
 
 def main_reference(args):
@@ -239,6 +323,24 @@ def main_ours(args):
         cpu_extra = {"threads_1": cpu_port_rate([c1, r1, c2, r2, b], img1, img2, s, angles, max(200, args.cpu_sample // 40), 1)[0],
                      "threads_5_reference_default": cpu_port_rate([c1, r1, c2, r2, b], img1, img2, s, angles,
                                                                   max(500, args.cpu_sample // 8), 5)[0]}
+
+    # the reference's whole pattern_matching on configs[0], in a child process (its fork Pool and cv2 stay away from CUDA)
+    ref_drop_in = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline and not args.no_configs and cpu_kind() == "reference":
+        import subprocess
+        import tempfile
+        npz = os.path.join(tempfile.mkdtemp(prefix="sid_bench_"), "matches.npz")
+        try:
+            child = subprocess.run([sys.executable, os.path.abspath(__file__), "--drop-in-reference", npz], stdout=subprocess.PIPE,
+                                   stderr=subprocess.PIPE, text=True, timeout=600)
+            lines = [l for l in child.stdout.splitlines() if l.startswith("{")]
+            if child.returncode == 0 and lines:
+                ref_drop_in = json.loads(lines[-1])
+                ref_drop_in["npz"] = npz
+            else:
+                sys.stderr.write("drop-in reference child failed: %s\n" % child.stderr[-800:])
+        except (OSError, subprocess.SubprocessError, ValueError) as exc:
+            sys.stderr.write("drop-in reference child failed: %r\n" % (exc,))
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this benchmark has no CPU path; use --impl reference)")
@@ -412,6 +514,13 @@ def main_ours(args):
                 configs[name]["first_guess"] = fg_note
         ctx.set_stream(None)
         ctx.set_pair(img1p, img2p)
+    drop_in = None
+    if ref_drop_in is not None:
+        try:
+            drop_in = drop_in_block(syn, ref_drop_in)
+        except Exception as exc:            # reported, never fatal for the headline line
+            drop_in = {"error": repr(exc)}
+        ctx.set_pair(img1p, img2p)
 
     line = None
     if rank == 0:
@@ -508,7 +617,7 @@ def main_ours(args):
                                 "upload in row bands overlapped with the fused kernel"},
                 "e2e_pageable": e2e_pageable,
                 "roofline": roofline, "roofline_fma": roofline_fma, "cpu_baseline": cpu, "parity": parity,
-                "configs": configs, "strong": strong}
+                "configs": configs, "strong": strong, "drop_in": drop_in}
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -542,7 +651,8 @@ if __name__ == "__main__":
     buf = io.StringIO()
     with JsonOnlyStdout():
         with contextlib.redirect_stdout(buf):
-            rc = main_reference(a) if a.impl == "reference" else main_ours(a)
+            rc = (drop_in_reference_child(a.drop_in_reference) if a.drop_in_reference
+                  else main_reference(a) if a.impl == "reference" else main_ours(a))
     line = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
     if line:
         print(line[-1], flush=True)

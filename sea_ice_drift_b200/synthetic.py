@@ -118,25 +118,31 @@ def make_config(name, seed=0, side=None, grid=None):
     return (img1, img2) + pts + (cfg,)
 
 
-def orb_first_guess_inputs(img1, img2, n_side, img_size, n_features=20000, ratio_test=0.6, inset=100):
-    """BASELINE configs[0] as the reference runs it: the per-point arrays of the hot loop from a real ORB first guess --
-    cv2.ORB keypoints with the reference's detector settings (ftlib.py:26-62), this package's GPU Hamming matcher + Lowe
-    ratio test (``ftlib.get_match_coords``), then ``pmlib.prepare_first_guess`` with the reference's default borders
-    (20 ... 50 px by the distance to the nearest keypoint, pmlib.py:249-324).  Returns c1, r1, c2fg, r2fg, border of the
-    grid points whose windows lie inside the images (the reference's ``gpi`` mask, pmlib.py:419-426)."""
+def orb_matches(img1, img2, n_features=20000, ratio_test=0.6):
+    """Feature-tracking matches x1, y1, x2, y2 (pixels) for BASELINE configs[0] ("ORB first guess"): cv2.ORB keypoints with
+    the reference's detector settings (ftlib.py:26-62), this package's GPU Hamming matcher + Lowe ratio test
+    (``ftlib.get_match_coords``), and an outlier rejection (the reference's lstsq_filter, ftlib.py:203-234, fits a plane
+    to the displacements; the synthetic drift is smooth, so a median test does the same job here)."""
     import cv2
-    from . import ftlib, pmlib
+    from . import ftlib
     cv2.setRNGSeed(0)
     det = cv2.ORB_create()
     det.setEdgeThreshold(34); det.setMaxFeatures(n_features); det.setNLevels(7); det.setPatchSize(34)
     kp1, d1 = det.detectAndCompute(img1, None)
     kp2, d2 = det.detectAndCompute(img2, None)
     x1, y1, x2, y2 = ftlib.get_match_coords(kp1, d1, kp2, d2, ratio_test=ratio_test)
-    # outlier rejection (the reference's lstsq_filter, ftlib.py:203-234, fits a plane to the displacements; the synthetic
-    # drift is smooth, so a median test does the same job here)
     du, dv = x2 - x1, y2 - y1
     keep = (np.abs(du - np.median(du)) < 30.0) & (np.abs(dv - np.median(dv)) < 30.0)
-    x1, y1, x2, y2 = x1[keep], y1[keep], x2[keep], y2[keep]
+    return x1[keep], y1[keep], x2[keep], y2[keep]
+
+
+def orb_first_guess_inputs(img1, img2, n_side, img_size, inset=100, matches=None):
+    """BASELINE configs[0] as the reference runs it: the per-point arrays of the hot loop from a real ORB first guess --
+    ``orb_matches`` then ``pmlib.prepare_first_guess`` with the reference's default borders (20 ... 50 px by the distance to
+    the nearest keypoint, pmlib.py:249-324).  Returns c1, r1, c2fg, r2fg, border of the grid points whose windows lie
+    inside the images (the reference's ``gpi`` mask, pmlib.py:419-426)."""
+    from . import pmlib
+    x1, y1, x2, y2 = matches if matches is not None else orb_matches(img1, img2)
     n1, n2 = ArrayDomain(img1), ArrayDomain(img2)
     gx, gy = np.meshgrid(np.linspace(inset, img1.shape[1] - inset, n_side), np.linspace(inset, img1.shape[0] - inset, n_side))
     c1, r1 = gx.ravel(), gy.ravel()
