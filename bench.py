@@ -226,6 +226,44 @@ def drop_in_block(syn, ref_line):
                     "generic position (any real geolocation) and first_guess='device' use the triangulation-free device interpolant"}
 
 
+def drop_in_ew_block(syn, img1, img2, angles, n_keypoints=50000, grid=200):
+    """The same call at the headline size: pattern_matching on the resident EW-sized pair (plain NumPy images, so the call
+    uploads them), 50 000 synthetic feature-tracking matches in generic (non-integer) position that follow the known drift
+    with 0.8 px noise, 200 x 200 grid, angles [-3, 0, 3].  The reference is not run here (prepare_first_guess alone takes
+    ~24 s at this size)."""
+    import contextlib
+    import io
+    from sea_ice_drift_b200 import pmlib
+    rng = np.random.default_rng(7)
+    side = img1.shape[0]
+    m = syn.rotation_matrix(img1.shape, syn.CONFIGS["cfg2"]["warp"][1])
+    kx, ky = rng.uniform(40, side - 40, n_keypoints), rng.uniform(40, side - 40, n_keypoints)
+    k2x, k2y = syn.apply_affine(m, kx, ky)
+    k2x, k2y = k2x + rng.normal(0, 0.8, n_keypoints), k2y + rng.normal(0, 0.8, n_keypoints)
+    n1, n2 = syn.ArrayDomain(img1), syn.ArrayDomain(img2)
+    gx, gy = np.meshgrid(np.linspace(150, side - 150, grid), np.linspace(150, side - 150, grid))
+    lon, lat = n2.transform_points(gx, gy)
+    ts, res = [], None
+    for _ in range(5):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = pmlib.pattern_matching(lon, lat, n1, kx, ky, n2, k2x, k2y, angles=angles, img_size=35)
+        ts.append(time.perf_counter() - t0)
+    mine = float(np.median(ts[1:]))
+    valid = int(np.isfinite(res[0]).sum())
+    # known answer: the drift of the synthetic pair at the grid points (minus the reference's -1 px template-centre bias)
+    ok = np.isfinite(res[0])
+    c2, r2 = n2.transform_points(res[5][ok], res[6][ok], 1)
+    c1g, r1g = n1.transform_points(lon[ok], lat[ok], 1)
+    tx, ty = syn.apply_affine(m, c1g, r1g)
+    err = float(np.median(np.hypot(c2 - (tx - 1), r2 - (ty - 1))))
+    return {"call": "pattern_matching(lon, lat, n1, x1, y1, n2, x2, y2, angles=[-3, 0, 3], img_size=35): %d x %d NumPy pair, %d matches "
+                    "in generic position, %d x %d grid" % (side, side, n_keypoints, grid, grid),
+            "ms": mine * 1e3, "first_call_ms": ts[0] * 1e3, "valid": valid, "vectors_per_s": valid / mine,
+            "median_error_px_vs_known_drift": err,
+            "reference": "not run (prepare_first_guess alone: 23.8 s at this size, BASELINE.md section 2; the per-point loop: cpu_baseline)"}
+
+
 def main_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (see module doc)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -521,6 +559,13 @@ def main_ours(args):
         except Exception as exc:            # reported, never fatal for the headline line
             drop_in = {"error": repr(exc)}
         ctx.set_pair(img1p, img2p)
+    drop_in_ew = None
+    if world == 1 and not args.no_configs and args.workload == "cfg2":
+        try:
+            drop_in_ew = drop_in_ew_block(syn, img1, img2, angles, grid=args.grid or 200)
+        except Exception as exc:
+            drop_in_ew = {"error": repr(exc)}
+        ctx.set_pair(img1p, img2p)
 
     line = None
     if rank == 0:
@@ -617,7 +662,7 @@ def main_ours(args):
                                 "upload in row bands overlapped with the fused kernel"},
                 "e2e_pageable": e2e_pageable,
                 "roofline": roofline, "roofline_fma": roofline_fma, "cpu_baseline": cpu, "parity": parity,
-                "configs": configs, "strong": strong, "drop_in": drop_in}
+                "configs": configs, "strong": strong, "drop_in": drop_in, "drop_in_ew": drop_in_ew}
     ctx.close()
     if world > 1:
         dist.barrier()
