@@ -185,6 +185,13 @@ bool make_window_tensor_map(sid_ctx *ctx, CUtensorMap *map, int box_w, int box_h
 }
 
 // shared launch path of sid_run / sid_run_device
+// Largest shared-memory footprint of pm_tail_kernel for which the tail is split off the correlation kernel
+// (SID_PM_TAIL_SMEM_KB overrides; 52 KB = at least 4 tail CTAs per SM)
+size_t tail_split_limit() {
+    if (const char *e = getenv("SID_PM_TAIL_SMEM_KB")) { const int kb = atoi(e); if (kb > 0) return (size_t)kb * 1024; }
+    return (size_t)52 * 1024;
+}
+
 int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1, const double *d_c2fg,
               const double *d_r2fg, const double *d_border, const int *d_order, int max_border, int typ_border,
               int img_size, int n_angles, const double *d_angles, const double *d_tab, int rot_order,
@@ -219,7 +226,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     const bool imma = !(path_env && strcmp(path_env, "dp4a") == 0);
     const bool smth = (flags & SID_HES_SMTH) != 0;
     // Split tail: peak statistics in a second, light kernel when the result map fits its shared memory
-    bool split_tail = pm_tail_smem_bytes(a.max_rr, smth) <= 52 * 1024;       // >= 4 tail CTAs per SM; larger maps measured
+    bool split_tail = pm_tail_smem_bytes(a.max_rr, smth) <= tail_split_limit();       // >= 4 tail CTAs per SM; larger maps measured
                                                                              // faster with the fused tail (cfg1: 1.10 vs 1.21 ms)
     if (const char *e = getenv("SID_PM_SPLIT_TAIL")) if (e[0] == '0') split_tail = false;
     alignas(64) CUtensorMap tmap;
@@ -659,7 +666,7 @@ int ws_border_limit(sid_ctx *ctx, int s, int n_angles, unsigned flags, int max_b
     for (int b = std::min(max_border, 40); b >= 1; --b) {
         const int Wmax = 2 * hws + 2 * b + 1, Rmax = Wmax - s + 1;
         if (Rmax < 2) break;
-        if (pm_tail_smem_bytes(Rmax * Rmax, smth) > 52 * 1024) continue;
+        if (pm_tail_smem_bytes(Rmax * Rmax, smth) > tail_split_limit()) continue;
         PmWsCfg g;
         memset(&g, 0, sizeof g);
         // the launch pads the angle planes for ITS typical map width (<= 31 words each): try the worst case, so that a
@@ -963,7 +970,7 @@ int run_host(sid_ctx *ctx, const HostPair *pair, int64_t n, const double *c1, co
         auto rr_of = [&](int b) { const int R = 2 * (img_size / 2) + 2 * b + 1 - img_size + 1; return R * R; };
         const bool smth = (flags & SID_HES_SMTH) != 0;
         const int rr_big = rr_of(max_border), rr_small = rr_of(small_max);
-        ctx->tail_region_stride = (size_t)(((pm_tail_smem_bytes(rr_big, smth) <= 52 * 1024 ? rr_big : rr_small) + 3) & ~3);
+        ctx->tail_region_stride = (size_t)(((pm_tail_smem_bytes(rr_big, smth) <= tail_split_limit() ? rr_big : rr_small) + 3) & ~3);
     }
     const bool two_streams = pair && nbands > 1;
     if (two_streams) {
@@ -1074,7 +1081,7 @@ int sid_run_device(sid_ctx *ctx, int64_t n, const double *d_c1, const double *d_
         if (n_small >= 256 && n_big > 0) {
             auto rr_of = [&](int b) { const int R = 2 * (img_size / 2) + 2 * b + 1 - img_size + 1; return R * R; };
             const bool smth = (flags & SID_HES_SMTH) != 0;
-            ctx->tail_region_stride = (size_t)(((pm_tail_smem_bytes(rr_of(max_border), smth) <= 52 * 1024 ? rr_of(max_border) : rr_of(limit)) + 3) & ~3);
+            ctx->tail_region_stride = (size_t)(((pm_tail_smem_bytes(rr_of(max_border), smth) <= tail_split_limit() ? rr_of(max_border) : rr_of(limit)) + 3) & ~3);
             ctx->tail_hint_n = n;
             rc = launch_pm(ctx, n_big, d_c1, d_r1, d_c2fg, d_r2fg, d_border, d_big, max_border, max_border, img_size,
                            n_angles, d_angles, d_tab, rot_order, flags, d_out, d_status, nullptr, 0, 0);
