@@ -338,7 +338,8 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
                 tg.mma_sums = 1; tg.sq_off = (int)maps_off; tg.wsq_off = (int)scratch;
             }
         }
-        if (smem > (size_t)ctx->max_smem_optin - 4096) use_tc = false;      // window too large: legacy kernels
+        if (smem > (size_t)ctx->max_smem_optin - 4096 - (smem_scratch ? 0 : 8192)) use_tc = false;      // window too large: legacy kernels
+                                                                          // (the global-scratch variant has 8 KB more static shared memory)
     }
     if (!use_tc) {
     // window staging by TMA when the padded window (+15 bytes: the box must start 16-byte aligned) fits one

@@ -447,6 +447,149 @@ __device__ __forceinline__ float gauss_at(const float *__restrict__ f, int rows,
     return __double2float_rn(acc);
 }
 
+// ---- fast path of peak_statistics: hes_norm only, maps of at least 5 x 5 with an odd number of elements, CTAs of 128 / 256 /
+// 512 threads, a 2048-word shared-memory histogram.  Same values as the general path below, three sweeps over the map
+// instead of six: the Hessian sweep also accumulates the sum (np.std's mean) and the first radix-select histogram; the
+// second sweep accumulates the squared deviations and the second histogram; a third sweep collects the (<= 64) values
+// sharing the median's upper 20 bits.  hypot() is never negative, so a value's bit pattern is its sortable key (digits:
+// bits 30..21 | 20..11 | 10..0).  The FP64 sums of float32 addends are exact for the map sizes of the split tail whatever the
+// order and differ from the sequential order by < 1 ulp(double) for the largest maps -- far below the float32 rounding that
+// follows -- which is why the kernels and the CPU restatement used by the tests agree bit for bit.
+// Rank search over 1024 bins (1024 / blockDim.x per thread): the thread owning the bin of rank kk writes sel = {bin, rank
+// inside it, population of the bin, 0}.  Two barriers inside.
+__device__ __forceinline__ void fast_rank_search(const uint32_t *__restrict__ hist, uint32_t kk, BlockScratch &bs) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int per = 1024 / nt;                       // 8, 4 or 2
+    uint32_t h[8];
+    uint32_t sum = 0;
+    if (per == 8) {
+        const uint4 h0 = reinterpret_cast<const uint4 *>(hist)[2 * tid], h1 = reinterpret_cast<const uint4 *>(hist)[2 * tid + 1];
+        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = j < per ? hist[tid * per + j] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += h[j];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) bs.wtot[warp] = incl;
+    __syncthreads();
+    uint32_t excl = incl - sum;
+    for (int w = 0; w < warp; ++w) excl += bs.wtot[w];
+    if (kk >= excl && kk < excl + sum) {
+        uint32_t c = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (kk >= c && kk < c + h[j]) { bs.sel[0] = (uint32_t)(tid * per + j); bs.sel[1] = kk - c; bs.sel[2] = h[j]; bs.sel[3] = 0u; }
+            c += h[j];
+        }
+    }
+    __syncthreads();
+}
+
+// `hist`: 2048 words of shared memory (any contents).  Returns (hes[peak] - median(hes)) / std(hes); every thread calls it.
+__device__ float hes_norm_fast(const float *__restrict__ map, int rows, int cols, int peak_idx, float *__restrict__ hes,
+                               uint32_t *__restrict__ hist, BlockScratch &bs) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5, n = rows * cols;
+    for (int k = tid; k < 512; k += nt) reinterpret_cast<uint4 *>(hist)[k] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    double dsum = 0.0;
+    // one Hessian value per lane and call (all 32 lanes call together): store, sum, first histogram (warp-aggregated:
+    // the values of a map fall into a handful of the 1024 exponent bins)
+    auto emit = [&](bool valid, int k, float v) {
+        uint32_t bin = 0xffffffffu;
+        if (valid) { hes[k] = v; dsum += (double)v; bin = __float_as_uint(v) >> 21; }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin & 1023u], (uint32_t)__popc(peers));
+    };
+    {   // interior: branch-free 5-point stencils, the rounding sequence of np.gradient(np.gradient(.)) away from the edges
+        const int iw = cols - 4, ni = (rows - 4) * iw;
+        const int idy = nt / iw, idx = nt - idy * iw;
+        int y = tid / iw, x = tid - y * iw;
+        for (int k = tid; k - tid < ni; k += nt) {
+            const bool valid = k < ni;
+            float v = 0.0f;
+            const int o = (y + 2) * cols + (x + 2);
+            if (valid) {
+                const float *p = map + o;
+                const float c = p[0];
+                const float gxp = __fmul_rn(__fsub_rn(p[2], c), 0.5f), gxm = __fmul_rn(__fsub_rn(c, p[-2]), 0.5f);
+                const float gyp = __fmul_rn(__fsub_rn(p[2 * cols], c), 0.5f), gym = __fmul_rn(__fsub_rn(c, p[-2 * cols]), 0.5f);
+                const double a2 = (double)__fmul_rn(__fsub_rn(gxp, gxm), 0.5f), b2 = (double)__fmul_rn(__fsub_rn(gyp, gym), 0.5f);
+                v = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(a2, a2), __dmul_rn(b2, b2))));
+            }
+            emit(valid, o, v);
+            x += idx; y += idy; if (x >= iw) { x -= iw; ++y; }
+        }
+        // border frame: two rows top and bottom, two columns left and right
+        const int nb = 4 * cols + 4 * (rows - 4);
+        for (int k = tid; k - tid < nb; k += nt) {
+            const bool valid = k < nb;
+            int yy = 0, xx = 0;
+            if (k < 4 * cols) { const int r = k / cols; xx = k - r * cols; yy = r < 2 ? r : rows - 4 + r; }
+            else { const int q = k - 4 * cols, r = q >> 2, ci = q & 3; yy = r + 2; xx = ci < 2 ? ci : cols - 4 + ci; }
+            float v = 0.0f;
+            if (valid) v = hessian_at(map, rows, cols, yy, xx);
+            emit(valid, yy * cols + xx, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) bs.red[warp] = dsum;
+    __syncthreads();                                   // hes, hist[0..1023] and red are complete
+    double tot = 0.0;
+    for (int w = 0; w < nw; ++w) tot += bs.red[w];
+    const float mean = __double2float_rn(tot / (double)n);
+    fast_rank_search(hist, (uint32_t)(n / 2), bs);
+    const uint32_t b1 = bs.sel[0], kk1 = bs.sel[1];
+    // second sweep: squared deviations (np.std) + second histogram over the values in bin b1
+    double q = 0.0;
+    for (int i = tid; i < n; i += nt) {
+        const float v = hes[i];
+        const float dv = __fsub_rn(v, mean);
+        q += (double)__fmul_rn(dv, dv);
+        const uint32_t u = __float_as_uint(v);
+        if ((u >> 21) == b1) atomicAdd(&hist[1024u + ((u >> 11) & 1023u)], 1u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) bs.red[16 + warp] = q;
+    __syncthreads();
+    double qt = 0.0;
+    for (int w = 0; w < nw; ++w) qt += bs.red[16 + w];
+    const float sd = __fsqrt_rn(__double2float_rn(qt / (double)n));
+    fast_rank_search(hist + 1024, kk1, bs);
+    const uint32_t prefix = (b1 << 10) | bs.sel[0], kk2 = bs.sel[1], pop = bs.sel[2];
+    float med;
+    if (pop <= 64u) {
+        for (int i = tid; i < n; i += nt) {
+            const uint32_t u = __float_as_uint(hes[i]);
+            if ((u >> 11) == prefix) bs.cand[atomicAdd(&bs.sel[3], 1u)] = u;
+        }
+        __syncthreads();
+        if (tid < (int)pop) {
+            const uint32_t mine = bs.cand[tid];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < pop; ++j) {
+                const uint32_t o = bs.cand[j];
+                rank += (o < mine) || (o == mine && j < (uint32_t)tid);
+            }
+            if (rank == kk2) bs.sel[0] = mine;
+        }
+        __syncthreads();
+        med = __uint_as_float(bs.sel[0]);
+        __syncthreads();                               // bs.sel is free again
+    } else {
+        med = block_select_wide(hes, n, n / 2, hist, bs);          // many values share 20 bits (flat maps): the general select
+    }
+    return __fdiv_rn(__fsub_rn(hes[peak_idx], med), sd);
+}
+
 // Tail of rotate_and_match (reference pmlib.py:167-172): Hessian at the peak and the
 // optional normalisations.  `best` is the winning NCC map; tmp_a/tmp_b/hes are scratch
 // maps of the same size.  Every thread of the CTA calls this; results valid in all.
@@ -456,6 +599,12 @@ __device__ PeakStats peak_statistics(const float *__restrict__ best, int rows, i
                                      float *__restrict__ tmp_a, float *__restrict__ tmp_b, float *__restrict__ hes,
                                      BlockScratch &bs, uint32_t *wide_hist = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x, n = rows * cols;
+    if (flags == 1u && wide_hist != nullptr && rows >= 5 && cols >= 5 && (n & 1) && (nt == 128 || nt == 256 || nt == 512)) {
+        PeakStats fast;
+        fast.r = peak_r;
+        fast.h = hes_norm_fast(best, rows, cols, peak_idx, hes, wide_hist, bs);
+        return fast;
+    }
     const int y_first = tid / cols, x_first = tid - y_first * cols, dy = nt / cols, dx = nt - dy * cols;
     const float *src = best;
     if (flags & 2u) {               // hes_smth

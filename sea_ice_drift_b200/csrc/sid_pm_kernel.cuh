@@ -729,133 +729,6 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
     }
 }
 
-// ---- pm_tail_kernel's fast path (hes_norm only, maps of at least 5 x 5 with an odd number of elements, 128 threads) ----
-// Same values as peak_statistics (sid_common.cuh), fewer sweeps over the map: the Hessian sweep also accumulates the sum
-// (np.std's mean) and the first radix-select histogram; the second sweep accumulates the squared deviations and the second
-// histogram; a third sweep collects the (<= 64) values sharing the median's upper 20 bits.  hypot() is never negative, so a
-// value's bit pattern is its sortable key (digits: bits 30..21 | 20..11 | 10..0).  The sums are exact in FP64 for maps of
-// this size whatever the order (24-bit addends, < 2^11 of them, exponent spread < 2^17), which is why the fused kernels,
-// this path and the CPU restatement used by the tests agree bit for bit.
-// Rank search over 1024 bins (8 per thread): the thread owning the bin of rank kk writes sel = {bin, rank inside it,
-// population of the bin, 0}.  Two barriers inside.
-__device__ __forceinline__ void tail_rank_search(const uint32_t *__restrict__ hist, uint32_t kk, BlockScratch &bs) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint4 h0 = reinterpret_cast<const uint4 *>(hist)[2 * tid], h1 = reinterpret_cast<const uint4 *>(hist)[2 * tid + 1];
-    const uint32_t h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    const uint32_t sum = (h0.x + h0.y) + (h0.z + h0.w) + (h1.x + h1.y) + (h1.z + h1.w);
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) bs.wtot[warp] = incl;
-    __syncthreads();
-    uint32_t excl = incl - sum;
-    for (int w = 0; w < warp; ++w) excl += bs.wtot[w];
-    if (kk >= excl && kk < excl + sum) {
-        uint32_t c = excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (kk >= c && kk < c + h[j]) { bs.sel[0] = 8u * tid + j; bs.sel[1] = kk - c; bs.sel[2] = h[j]; bs.sel[3] = 0u; }
-            c += h[j];
-        }
-    }
-    __syncthreads();
-}
-
-// `hist`: 2048 words, zeroed by the caller before its last barrier.  Returns (hes[peak] - median(hes)) / std(hes).
-__device__ float tail_hes_norm_fast(const float *__restrict__ map, int rows, int cols, int peak_idx, float *__restrict__ hes,
-                                    uint32_t *__restrict__ hist, BlockScratch &bs) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = rows * cols;
-    constexpr int NT = 128;
-    double dsum = 0.0;
-    // one Hessian value per lane and call (all 32 lanes call together): store, sum, first histogram (warp-aggregated:
-    // the values of a map fall into a handful of the 1024 exponent bins)
-    auto emit = [&](bool valid, int k, float v) {
-        uint32_t bin = 0xffffffffu;
-        if (valid) { hes[k] = v; dsum += (double)v; bin = __float_as_uint(v) >> 21; }
-        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-        if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin & 1023u], (uint32_t)__popc(peers));
-    };
-    {   // interior: branch-free 5-point stencils, the rounding sequence of np.gradient(np.gradient(.)) away from the edges
-        const int iw = cols - 4, ni = (rows - 4) * iw;
-        const int idy = NT / iw, idx = NT - idy * iw;
-        int y = tid / iw, x = tid - y * iw;
-        for (int k = tid; k - tid < ni; k += NT) {
-            const bool valid = k < ni;
-            float v = 0.0f;
-            const int o = (y + 2) * cols + (x + 2);
-            if (valid) {
-                const float *p = map + o;
-                const float c = p[0];
-                const float gxp = __fmul_rn(__fsub_rn(p[2], c), 0.5f), gxm = __fmul_rn(__fsub_rn(c, p[-2]), 0.5f);
-                const float gyp = __fmul_rn(__fsub_rn(p[2 * cols], c), 0.5f), gym = __fmul_rn(__fsub_rn(c, p[-2 * cols]), 0.5f);
-                const double a2 = (double)__fmul_rn(__fsub_rn(gxp, gxm), 0.5f), b2 = (double)__fmul_rn(__fsub_rn(gyp, gym), 0.5f);
-                v = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(a2, a2), __dmul_rn(b2, b2))));
-            }
-            emit(valid, o, v);
-            x += idx; y += idy; if (x >= iw) { x -= iw; ++y; }
-        }
-        // border frame: two rows top and bottom, two columns left and right
-        const int nb = 4 * cols + 4 * (rows - 4);
-        for (int k = tid; k - tid < nb; k += NT) {
-            const bool valid = k < nb;
-            int yy = 0, xx = 0;
-            if (k < 4 * cols) { const int r = k / cols; xx = k - r * cols; yy = r < 2 ? r : rows - 4 + r; }
-            else { const int q = k - 4 * cols, r = q >> 2, ci = q & 3; yy = r + 2; xx = ci < 2 ? ci : cols - 4 + ci; }
-            float v = 0.0f;
-            if (valid) v = hessian_at(map, rows, cols, yy, xx);
-            emit(valid, yy * cols + xx, v);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-    if (lane == 0) bs.red[warp] = dsum;
-    __syncthreads();                                   // hes, hist[0..1023] and red are complete
-    const float mean = __double2float_rn(((bs.red[0] + bs.red[1]) + (bs.red[2] + bs.red[3])) / (double)n);
-    tail_rank_search(hist, (uint32_t)(n / 2), bs);
-    const uint32_t b1 = bs.sel[0], kk1 = bs.sel[1];
-    // second sweep: squared deviations (np.std) + second histogram over the values in bin b1
-    double q = 0.0;
-    for (int i = tid; i < n; i += NT) {
-        const float v = hes[i];
-        const float dv = __fsub_rn(v, mean);
-        q += (double)__fmul_rn(dv, dv);
-        const uint32_t u = __float_as_uint(v);
-        if ((u >> 21) == b1) atomicAdd(&hist[1024u + ((u >> 11) & 1023u)], 1u);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (lane == 0) bs.red[4 + warp] = q;
-    __syncthreads();
-    const float sd = __fsqrt_rn(__double2float_rn(((bs.red[4] + bs.red[5]) + (bs.red[6] + bs.red[7])) / (double)n));
-    tail_rank_search(hist + 1024, kk1, bs);
-    const uint32_t prefix = (b1 << 10) | bs.sel[0], kk2 = bs.sel[1], pop = bs.sel[2];
-    float med;
-    if (pop <= 64u) {
-        for (int i = tid; i < n; i += NT) {
-            const uint32_t u = __float_as_uint(hes[i]);
-            if ((u >> 11) == prefix) bs.cand[atomicAdd(&bs.sel[3], 1u)] = u;
-        }
-        __syncthreads();
-        if (tid < (int)pop) {
-            const uint32_t mine = bs.cand[tid];
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < pop; ++j) {
-                const uint32_t o = bs.cand[j];
-                rank += (o < mine) || (o == mine && j < (uint32_t)tid);
-            }
-            if (rank == kk2) bs.sel[0] = mine;
-        }
-        __syncthreads();
-        med = __uint_as_float(bs.sel[0]);
-    } else {
-        med = block_select_wide(hes, n, n / 2, hist, bs);          // many values share 20 bits (flat maps): the general select
-    }
-    return __fdiv_rn(__fsub_rn(hes[peak_idx], med), sd);
-}
-
 // Peak statistics of one work item per CTA (reference pmlib.py:167-172, 209-210) on the map the fused kernel
 // handed over.  Light on registers and shared memory, so ~10 CTAs are resident per SM.
 constexpr int PM_TAIL_THREADS = 128;
@@ -875,16 +748,9 @@ __global__ void __launch_bounds__(PM_TAIL_THREADS) pm_tail_kernel(const PmArgs a
     const float4 *src = reinterpret_cast<const float4 *>(a.tail_maps + (size_t)blockIdx.x * a.tail_stride);
     // the producer wrote RR floats; the up to 3 floats behind them in the last vector are never used
     for (int k = tid; k < (RR + 3) >> 2; k += nt) reinterpret_cast<float4 *>(map)[k] = src[k];
-    const bool fast = a.flags == 1u && rec.RH >= 5 && rec.RW >= 5 && (RR & 1) && nt == 128;
-    if (fast) for (int k = tid; k < 512; k += nt) reinterpret_cast<uint4 *>(wide_hist)[k] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    PeakStats ps;
-    if (fast) {
-        ps.r = rec.best_r;
-        ps.h = tail_hes_norm_fast(map, rec.RH, rec.RW, rec.best_idx, hes, wide_hist, bs);
-    } else {
-        ps = peak_statistics(map, rec.RH, rec.RW, rec.best_idx, rec.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, bs, wide_hist);
-    }
+    // hes_norm-only maps take peak_statistics' three-sweep fast path (sid_common.cuh) on the 2048-word histogram
+    const PeakStats ps = peak_statistics(map, rec.RH, rec.RW, rec.best_idx, rec.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, bs, wide_hist);
     if (tid == 0) {
         const int bi = rec.best_idx / rec.RW, bj = rec.best_idx - bi * rec.RW;
         const double dr = (double)bi - (double)(rec.H - a.s) / 2.0;

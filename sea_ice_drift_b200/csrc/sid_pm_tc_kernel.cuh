@@ -795,8 +795,11 @@ pm_tc_kernel(const PmArgs a, const PmTcCfg g, const __grid_constant__ CUtensorMa
         float *tmp_a = maps + (size_t)(best_slot == 0 ? 1 : 0) * a.max_rr;
         float *hes = maps + (size_t)(nab + 1) * a.max_rr;
         float *tmp_b = maps + (size_t)(nab + 2) * a.max_rr;
+        // 2048-word histogram for the select of peak_statistics: the (dead) window statistics when the scratch is in shared
+        // memory, else 8 KB of static shared memory (large maps: the scratch lives in the L2-resident slab)
         uint32_t *wide_hist = nullptr;
         if constexpr (SMEM_SCRATCH) { if ((size_t)a.max_rr * 8 >= 2048 * 4) wide_hist = reinterpret_cast<uint32_t *>(wden); }
+        else { __shared__ __align__(16) uint32_t tail_hist_s[2048]; wide_hist = tail_hist_s; }
         const PeakStats ps = peak_statistics(best, RH, RW, best_idx, S.best_r, a.flags, a.gw, tmp_a, tmp_b, hes, S.bs, wide_hist);
         if (tid == 0) {
             const int bi = best_idx / RW, bj = best_idx - bi * RW;
