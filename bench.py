@@ -634,7 +634,7 @@ def main_ours(args):
                     "note": "algorithmic FLOPs = sum over points and angles of 2 s^2 R^2 (SURVEY 8d), multiply-adds of the direct-form "
                             "correlation only; they run as tcgen05.mma kind::i8 (u8 x u8 -> s32, TMEM accumulators; measured pipe rate "
                             "7949 MAC/clk/SM = u8_tcgen05_peak, profiles/r02_tcgen05_i8_rates.txt). pm_ws_kernel (default for search "
-                            "radii <= 20 at img_size 35) is a warp-specialised pipeline, one CTA of 28 warps per SM: the tensor pipe is ~15 % busy and no "
+                            "radii <= 22 at img_size 35) is a warp-specialised pipeline, one CTA of 28 warps per SM: the tensor pipe is ~15 % busy and no "
                             "pipe is saturated; the time is set by the instruction latency chains of the gather / window-statistics / "
                             "normalisation roles at 28 resident warps (ncu: 13 cycles per issued warp instruction, IPC 2.1; "
                             "profiles/r02_pm_ws_ncu_roles.txt). BASELINE.json's own figure, the fraction of the FP32-FMA roofline, is in "

@@ -287,16 +287,21 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     PmTcCfg tg;
     memset(&tg, 0, sizeof tg);
     bool use_tc = false;
-    // warp-specialised pipeline kernel (sid_pm_ws_kernel.cuh): small result maps (geometry: radius <= 24; its shared-memory layout fits 227 KB up to radius 20 at s = 35), needs the split tail
+    // warp-specialised pipeline kernel (sid_pm_ws_kernel.cuh): small result maps (geometry: radius <= 24; its shared-memory layout fits 227 KB up to radius 20 at s = 35, 22 with two sets of window statistics), needs the split tail
     PmWsCfg wg;
     memset(&wg, 0, sizeof wg);
     alignas(64) CUtensorMap tmap1;                  // image 1: the patch the templates of a point are sampled from
     memset(&tmap1, 0, sizeof tmap1);
     bool use_ws = false;
-    if (want_ws && split_tail && pm_ws_geometry(s, Rmax, Wmax, n_angles, a.max_rr, wg, 2 * typ_border + (Wmax - 2 * max_border) - s + 1) &&
-        (size_t)wg.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows) &&
-        make_window_tensor_map(ctx, &tmap1, wg.pbw, wg.pbh, 1))
-        use_ws = true;
+    if (want_ws && split_tail) {
+        // three sets of window statistics where they fit the shared memory, else two (radius 21 ... 22 at img_size 35)
+        const int rtyp = 2 * typ_border + (Wmax - 2 * max_border) - s + 1;
+        bool fits = false;
+        for (int nstat = WS_NSTAT; nstat >= 2 && !fits; --nstat)
+            fits = pm_ws_geometry(s, Rmax, Wmax, n_angles, a.max_rr, wg, rtyp, nstat) && (size_t)wg.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin;
+        if (fits && make_window_tensor_map(ctx, &tmap, 16, wg.load_rows) && make_window_tensor_map(ctx, &tmap1, wg.pbw, wg.pbh, 1))
+            use_ws = true;
+    }
     if (use_ws) {
         a.tma = 1; a.ab = wg.nab;
         int rc = reserve(ctx, ctx->counter, 256);
@@ -318,8 +323,8 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
         if (grid > n) grid = n;
         if (grid < 1) grid = 1;
         if (getenv("SID_DEBUG"))
-            fprintf(stderr, "[sid] launch: ws smem=%d nab=%d ks=%d npairs=%d nslots=%d slot_bytes=%d npanels=%d wrows=%d n16max=%d grid=%lld\n",
-                    wg.smem_bytes, wg.nab, wg.ks, wg.npairs, wg.nslots, wg.slot_bytes, wg.npanels, wg.wrows, wg.n16max, grid);
+            fprintf(stderr, "[sid] launch: ws smem=%d nstat=%d nab=%d ks=%d npairs=%d nslots=%d slot_bytes=%d npanels=%d wrows=%d n16max=%d grid=%lld\n",
+                    wg.smem_bytes, wg.nstat, wg.nab, wg.ks, wg.npairs, wg.nslots, wg.slot_bytes, wg.npanels, wg.wrows, wg.n16max, grid);
 #ifdef SID_WS_PROF
         if ((rc = reserve(ctx, ctx->scratch, (size_t)grid * 6 * 8 * 8))) return rc;
         CU(cudaMemsetAsync(ctx->scratch.p, 0, (size_t)grid * 6 * 8 * 8, st));
@@ -726,10 +731,11 @@ int ws_border_limit(sid_ctx *ctx, int s, int n_angles, unsigned flags, int max_b
         memset(&g, 0, sizeof g);
         // the launch pads the angle planes for ITS typical map width (<= 31 words each): try the worst case, so that a
         // border this function accepts is never refused by the launch
-        bool ok = pm_ws_geometry(s, Rmax, Wmax, n_angles, Rmax * Rmax, g) && (size_t)g.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin;
+        // (the smallest layout: two sets of window statistics)
+        bool ok = pm_ws_geometry(s, Rmax, Wmax, n_angles, Rmax * Rmax, g, 0, 2) && (size_t)g.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin;
         if (ok && (size_t)g.smem_bytes + 2048 + 31 * 4 * 2 * 3 > (size_t)ctx->max_smem_optin) {
             for (int rt = 2; rt <= Rmax && ok; ++rt)
-                ok = pm_ws_geometry(s, Rmax, Wmax, n_angles, Rmax * Rmax, g, rt) && (size_t)g.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin;
+                ok = pm_ws_geometry(s, Rmax, Wmax, n_angles, Rmax * Rmax, g, rt, 2) && (size_t)g.smem_bytes + 2048 <= (size_t)ctx->max_smem_optin;
         }
         if (ok) return b;
     }

@@ -39,7 +39,8 @@ namespace sid {
 constexpr int WS_THREADS = 896;           // 28 warps: control | 4 mma | 8 gather | 7 stats | 2 x 4 epilogue
 constexpr int WS_W_MMA = 1, WS_W_GATHER = 5, WS_W_STATS = 13, WS_W_EPI = 20;
 constexpr int WS_NST = 7 * 32;            // stats threads
-constexpr int WS_NSTAT = 3;               // sets of window statistics (stats warps run up to 3 points ahead of the epilogue)
+constexpr int WS_NSTAT = 3;               // sets of window statistics (stats warps run up to 3 points ahead of the epilogue);
+                                          // 2 where three do not fit the shared memory (PmWsCfg::nstat)
 constexpr int WS_NG = 8;                  // gather warps
 constexpr int WS_NWIN = 2;                // window ring (each slot: the search window of image 2 + the template patch of image 1)
 constexpr int WS_NENT = 8;                // point entries / template records
@@ -66,6 +67,7 @@ struct PmWsCfg {
     int nwords;       // 32-bit words per compact template row = ceil(s / 4)
     int tw;           // compact row pitch (words) = nwords + 2 (a zero word either side)
     int nslots;       // A ring depth
+    int nstat;        // sets of window statistics (3, or 2 for the largest maps)
     int lbo_a;        // bytes between K panels of an A slot
     int slot_bytes;
     int wrows;        // rows per window panel
@@ -84,7 +86,7 @@ struct PmWsCfg {
     int off_a, off_tpl, tpl_buf_words, off_stat, stat_bytes, off_hs, off_c, smem_bytes;
 };
 
-inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, PmWsCfg &g, int Rtyp = 0) {
+inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, PmWsCfg &g, int Rtyp = 0, int nstat = WS_NSTAT) {
     if (s < 2 || s > 112 || Rmax < 2) return false;
     if (Rmax + 1 > 64 || Rmax + 15 > 64 || Wmax > 256) return false;
     g.nab = n_angles < 3 ? n_angles : 3;
@@ -137,7 +139,8 @@ inline bool pm_ws_geometry(int s, int Rmax, int Wmax, int n_angles, int max_rr, 
     off = (off + 127) & ~(size_t)127;
     g.off_stat = (int)off;
     g.stat_bytes = (max_rr * 12 + 127) & ~127;           // wden f64 (its low words first hold the u32 sums of squares) | wsum u32
-    off += (size_t)WS_NSTAT * g.stat_bytes;
+    g.nstat = nstat < 2 ? 2 : (nstat > WS_NSTAT ? WS_NSTAT : nstat);
+    off += (size_t)g.nstat * g.stat_bytes;
     g.hs_words = Rmax * g.hp;
     g.off_hs = (int)off; off += (size_t)g.hs_words * 6;       // hq u32 | hs u16
     off = (off + 127) & ~(size_t)127;
@@ -667,8 +670,8 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
             if (e.done) break;
             const int W = e.W, H = e.H, xoff = e.x0 & 15;
             const int RH = H - s + 1, RW = W - s + 1;
-            const unsigned set = P % WS_NSTAT;
-            if (P >= WS_NSTAT) ws_wait<200u>(BAR(&B.stats_empty[set]), ((P / WS_NSTAT) - 1u) & 1u, __LINE__);
+            const unsigned set = P % (unsigned)g.nstat;
+            if (P >= (unsigned)g.nstat) ws_wait<200u>(BAR(&B.stats_empty[set]), ((P / (unsigned)g.nstat) - 1u) & 1u, __LINE__);
             WSP(2)
             double *wden = reinterpret_cast<double *>(ws_smem + g.off_stat + (size_t)set * g.stat_bytes);
             uint32_t *wsum = reinterpret_cast<uint32_t *>(wden + a.max_rr);
@@ -806,7 +809,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
         WSP_DECL
         for (unsigned n = 0; !leave; ++n) {
             const unsigned P = (unsigned)eg + 2u * n;
-            const unsigned sset = P % WS_NSTAT;
+            const unsigned sset = P % (unsigned)g.nstat;
             const double *wden = reinterpret_cast<const double *>(ws_smem + g.off_stat + (size_t)sset * g.stat_bytes);
             const uint32_t *wsum = reinterpret_cast<const uint32_t *>(wden + a.max_rr);
             float best_r = -INFINITY;
@@ -826,7 +829,7 @@ pm_ws_kernel(const PmArgs a, const PmWsCfg g, const __grid_constant__ CUtensorMa
                 if (b == 0) {
                     pt = tr.pt; pi = tr.pi; W = tr.W; H = tr.H; xoff = tr.x0 & 15;
                     RH = H - s + 1; RW = W - s + 1; RR = RH * RW;
-                    ws_wait<100u>(BAR(&B.stats_full[sset]), (P / WS_NSTAT) & 1u, __LINE__);
+                    ws_wait<100u>(BAR(&B.stats_full[sset]), (P / (unsigned)g.nstat) & 1u, __LINE__);
                 }
                 WSP(2)
                 const int a0 = b * per, nb = min(per, A_ - a0);
