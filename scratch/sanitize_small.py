@@ -30,3 +30,17 @@ tpl = ctx.get_template(img1, 300.5, 310.25, 2.0, 35)
 res = ctx.match_template(img2[200:300, 220:330], tpl)
 hes = ctx.get_hessian(res)
 print("ok2", np.isnan(out4[:, 0]).sum(), idx.shape, len(tri), tpl.shape, res.shape, float(hes.max()))
+# border classes (two launches per band, tail regions with one stride) through the banded, staged upload of pageable images,
+# and the two-statistics-set layout of pm_ws_kernel (borders 21..22)
+import os
+os.environ["SID_BANDS"] = "3"
+bmix = np.where(np.random.default_rng(5).random(b.size) < 0.8, 20.0, np.floor(np.random.default_rng(6).uniform(21, 40, b.size)))
+c1x, r1x, c2x, r2x = [np.tile(v, 8) for v in (c1, r1, c2, r2)]; bmx = np.tile(bmix, 8)
+out_mix = ctx.run_pair(img1, img2, c1x, r1x, c2x, r2x, bmx, 35, [-3, 0, 3], 0.0)
+del os.environ["SID_BANDS"]
+out_mix1 = ctx.run(c1x, r1x, c2x, r2x, bmx, 35, [-3, 0, 3], 0.0); name_mix = ctx.last_kernel_name
+assert np.array_equal(out_mix, out_mix1, equal_nan=True)
+b22 = np.floor(np.random.default_rng(7).uniform(21, 23, b.size))
+out_22 = ctx.run(c1, r1, c2, r2, b22, 35, [-3, 0, 3], 0.0); name_22 = ctx.last_kernel_name
+print("classes", name_mix, len(c1x), int((bmx <= 22).sum()), np.isnan(out_mix[:, 0]).sum(), "| two statistics sets", name_22, np.isnan(out_22[:, 0]).sum())
+assert "+ sid::pm_ws_kernel" in name_mix and name_22 == "sid::pm_ws_kernel", (name_mix, name_22)
