@@ -359,7 +359,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
 #endif
         const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
         if (int arc = allow_max_smem(ctx, (const void *)pm_tail_kernel)) return arc;
-        pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, st>>>(a);
+        pm_tail_kernel<<<(unsigned)n, pm_tail_threads(a.max_rr), tsm, st>>>(a);
         ctx->launches += 1;
         CU(cudaGetLastError());
         return SID_OK;
@@ -546,7 +546,7 @@ int launch_pm(sid_ctx *ctx, long long n, const double *d_c1, const double *d_r1,
     if (split_tail) {
         const size_t tsm = pm_tail_smem_bytes(a.max_rr, smth);
         if (int arc = allow_max_smem(ctx, (const void *)pm_tail_kernel)) return arc;
-        pm_tail_kernel<<<(unsigned)n, PM_TAIL_THREADS, tsm, st>>>(a);
+        pm_tail_kernel<<<(unsigned)n, pm_tail_threads(a.max_rr), tsm, st>>>(a);
         ctx->launches += 1;
         CU(cudaGetLastError());
     }

@@ -731,8 +731,9 @@ pm_points_kernel(const PmArgs a, const __grid_constant__ CUtensorMap tmap2) {
 
 // Peak statistics of one work item per CTA (reference pmlib.py:167-172, 209-210) on the map the fused kernel
 // handed over.  Light on registers and shared memory, so ~10 CTAs are resident per SM.
-constexpr int PM_TAIL_THREADS = 128;
-__global__ void __launch_bounds__(PM_TAIL_THREADS) pm_tail_kernel(const PmArgs a) {
+constexpr int PM_TAIL_THREADS = 128;            // small maps; 256 / 512 for larger ones (pm_tail_threads)
+constexpr int PM_TAIL_MAX_THREADS = 512;
+__global__ void __launch_bounds__(PM_TAIL_MAX_THREADS) pm_tail_kernel(const PmArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
     __shared__ BlockScratch bs;
     const PmTailRec rec = a.tail_recs[blockIdx.x];
@@ -763,6 +764,12 @@ __global__ void __launch_bounds__(PM_TAIL_THREADS) pm_tail_kernel(const PmArgs a
         o[4] = (double)ps.h;
         if (a.status) a.status[rec.pt] = 1;
     }
+}
+// CTA size of pm_tail_kernel by map size: a large map in shared memory leaves room for only two CTAs per SM, so each gets
+// more warps (SID_PM_TAIL_THREADS overrides; 128 / 256 / 512 take peak_statistics' fast path)
+inline int pm_tail_threads(int max_rr) {
+    if (const char *e = getenv("SID_PM_TAIL_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512) return v; }
+    return max_rr <= 2560 ? 128 : (max_rr <= 6144 ? 256 : 512);
 }
 inline size_t pm_tail_smem_bytes(int max_rr, bool smth) { return (size_t)((max_rr + 3) & ~3) * 4 * (2 + (smth ? 2 : 0)) + 2048 * 4; }
 
