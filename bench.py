@@ -15,8 +15,8 @@ One step = one pass of the hot path over the whole PM grid of one image pair.
             over the kernel's average duration, against the measured dense tensor peak of
             MEASURED_PEAKS.json (the multiply-adds run as tcgen05 kind::i8 MMAs); roofline_fma repeats it
             against the FP32-FMA peak that BASELINE.json's metric names.
-  configs : the other single-GPU BASELINE configurations (cfg1, cfg3, cfg4) at full size, device-resident; cfg1 with the
-            borders of a real ORB first guess.
+  configs : the other BASELINE configurations at full size: cfg1 (borders of a real ORB first guess), cfg3, cfg4
+            device-resident; cfg5 (time series) end to end through sharding.use_mcc_series, this GPU's share of the pairs.
   drop_in : the whole call a user of the reference makes -- pattern_matching(lon, lat, n1, x1, y1, n2, x2, y2) on
             configs[0] with NumPy images -- wall clock, next to the UNMODIFIED reference's pattern_matching on the same
             inputs (its own ORB matches; timed in a child process before CUDA is initialised).
@@ -551,6 +551,34 @@ def main_ours(args):
             if fg_note:
                 configs[name]["first_guess"] = fg_note
         ctx.set_stream(None)
+        # cfg5 (time series of EW pairs, 300 x 300 grid each) through sharding.use_mcc_series: every pair is uploaded inside
+        # the timed region (pinned host images), one table per pair comes back; end-to-end wall clock.  One GPU's share of
+        # the series: 4 pairs (the series cycles through the resident host pair; scratch/time_series.py runs all 16 at N > 1)
+        try:
+            from sea_ice_drift_b200 import sharding
+            c5 = dict(syn.CONFIGS["cfg5"])
+            if args.grid:
+                c5["grid"] = args.grid
+            m5 = syn.rotation_matrix(img1.shape, c5["warp"][1])
+            p5 = list(syn.hot_loop_inputs(img1, m5, c5["grid"], c5["img_size"], c5["border"], rank))
+            series = [(img1p, img2p) + tuple(p5)] * 4
+            sharding.use_mcc_series(series[:2], c5["img_size"], 0.0, angles=c5["angles"])            # warm-up (allocations)
+            best = None
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tabs = sharding.use_mcc_series(series, c5["img_size"], 0.0, angles=c5["angles"])
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            nvec = sum(len(t) for t in tabs)
+            configs["cfg5"] = {"workload": "cfg5: time series, %d of 16 pairs %dx%d on this GPU, %d-point PM grid each (300x300 requested), img_size=%d, "
+                                           "border=%s, angles=%s; sharding.use_mcc_series, every pair uploaded inside the timed region"
+                                           % (len(series), img1.shape[0], img1.shape[1], len(p5[0]), c5["img_size"], c5["border"], c5["angles"]),
+                               "points": int(nvec), "value": nvec / best, "unit": UNIT, "ms_per_pair": best * 1e3 / len(series),
+                               "timing": "end to end, host clock, best of 3", "tflops_equiv": None}
+        except Exception as exc:            # reported, never fatal for the headline line
+            configs["cfg5"] = {"error": repr(exc)}
         ctx.set_pair(img1p, img2p)
     drop_in = None
     if ref_drop_in is not None:
@@ -613,6 +641,8 @@ def main_ours(args):
         i8_peak = sm_count * 7949 * 2 * sm_max * 1e6 / 1e12       # tcgen05 kind::i8 measured: profiles/r02_tcgen05_i8_rates.txt
         if configs:
             for cdict in configs.values():
+                if cdict.get("tflops_equiv") is None:          # cfg5 is an end-to-end figure (uploads inside), no kernel roofline
+                    continue
                 cdict["roofline_frac"] = cdict["tflops_equiv"] / tensor_peak
                 cdict["frac_of_fp32_fma_peak"] = cdict["tflops_equiv"] / peak_tflops
         # main object: the correlation of the dominant kernel runs on the tensor pipe (exact u8 x u8 -> s32 IMMA), so the
