@@ -222,9 +222,9 @@ def use_mcc_series(pairs, img_size, alpha0=0.0, n_contexts=1, compute=None, gath
     callables returning one (lazy loading: a rank only ever touches its own pairs).  Pairs are dealt round-robin
     to the ranks of the process group (``shard_pairs``); inside a rank every pair goes through
     ``Context.run_pair`` (banded upload overlapped with the kernels).  ``n_contexts`` > 1 lets several contexts work
-    through the rank's pairs concurrently (threads); measured on B200 this is SLOWER than one context (13.2 vs
-    14.0 / 16.8 ms per EW pair for 1 / 2 / 3 contexts: the persistent kernels and band uploads of two pairs only
-    delay each other), so the default is 1.  Returns the list of (n_k, 5) tables ``[c2, r2, angle, r, h]`` in pair order -- complete on
+    through the rank's pairs concurrently (threads); measured on B200 this is SLOWER than one context (9.4 vs
+    11.0 ms per EW pair for 1 / 2 contexts at the end of round 2, 13.2 / 14.0 / 16.8 ms for 1 / 2 / 3 in round 1: the
+    persistent kernels and band uploads of two pairs only delay each other), so the default is 1.  Returns the list of (n_k, 5) tables ``[c2, r2, angle, r, h]`` in pair order -- complete on
     every rank when ``gather`` is true (one all-gather of the padded tables); with ``gather='root'`` only rank 0
     reads the gathered tables back (the other ranks keep ``None`` for foreign pairs, as with ``gather=False``) --
     the cheaper choice when one process writes the products, since the read-back is host-memory bound.
